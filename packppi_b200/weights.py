@@ -1,0 +1,91 @@
+"""`state_dict` layout of the reference model and a seeded random initialiser.
+
+Key names and shapes are those produced by `TDiffusionModule.__init__`
+(reference src/models/TorsionalDiffusion.py:39-68), so a trained reference checkpoint loads verbatim.
+The Google-Drive checkpoint is not available offline; benchmarks and parity tests use
+`make_state_dict(seed)`, which draws every tensor from its own `torch.Generator` so that the values do
+not depend on module construction order (xavier-uniform for matrices as TorsionalDiffusion.py:80-82,
+small uniform biases, LayerNorm gains near 1 so that gamma/beta are exercised).
+"""
+import math
+from collections import OrderedDict
+
+import torch
+
+H = 128          # hidden / node / edge feature width (configs/model/model_cfg/MpnnNet.yaml:1)
+NODE_IN = 51     # 35 + 16 time-embedding dims (encoder.py:76)
+EDGE_IN = 468    # 65 relpos + 400 RBF + 1 chain type + 2 dihedrals (encoder.py:236)
+N_POINTS = 8
+MSG_IN = 2 * H + H + 9 * N_POINTS  # 456 (layers.py:49)
+N_LAYERS = 3
+TOP_K = 32
+
+
+def shapes():
+    s = OrderedDict()
+
+    def lin(name, out, inp):
+        s[name + ".weight"] = (out, inp)
+        s[name + ".bias"] = (out,)
+
+    def ln(name):
+        s[name + ".weight"] = (H,)
+        s[name + ".bias"] = (H,)
+
+    lin("encoder.node_embedding", H, NODE_IN)
+    ln("encoder.norm_nodes")
+    lin("encoder.edge_embedding", H, EDGE_IN)
+    ln("encoder.norm_edges")
+    for l in range(N_LAYERS):
+        p = f"mpnn.mpnn_layers.{l}."
+        lin(p + "points_fn_node", 3 * N_POINTS, H)
+        lin(p + "points_fn_edge", 3 * N_POINTS, H)
+        for fn in ("node_message_fn", "edge_message_fn"):
+            lin(p + fn + ".W_in", H, MSG_IN)
+            lin(p + fn + ".W_inter.0", H, H)
+            lin(p + fn + ".W_out", H, H)
+        for i in range(4):
+            ln(p + f"norm.{i}")
+        for fn in ("node_dense", "edge_dense"):
+            lin(p + fn + ".W_in", 4 * H, H)
+            lin(p + fn + ".W_out", H, 4 * H)
+    lin("decoder_score.0.W_in", H // 2, H)
+    lin("decoder_score.0.W_out", H // 4, H // 2)
+    lin("decoder_score.2.W_in", H // 8, H // 4)
+    lin("decoder_score.2.W_out", 4, H // 8)
+    return s
+
+
+def num_parameters():
+    n = 0
+    for shp in shapes().values():
+        k = 1
+        for d in shp:
+            k *= d
+        n += k
+    return n
+
+
+def make_state_dict(seed=0, device="cpu"):
+    sd = OrderedDict()
+    for i, (name, shp) in enumerate(shapes().items()):
+        g = torch.Generator().manual_seed(1000003 * int(seed) + i)
+        if len(shp) == 2:
+            bound = math.sqrt(6.0 / (shp[0] + shp[1]))
+            w = (torch.rand(shp, generator=g) * 2 - 1) * bound
+        elif ".norm" in name and name.endswith(".weight"):
+            w = 1.0 + 0.1 * (torch.rand(shp, generator=g) * 2 - 1)
+        else:
+            w = 0.1 * (torch.rand(shp, generator=g) * 2 - 1)
+        sd[name] = w.to(torch.float32).to(device)
+    return sd
+
+
+def check_state_dict(sd):
+    exp = shapes()
+    missing = [k for k in exp if k not in sd]
+    if missing:
+        raise RuntimeError(f"state_dict is missing keys: {missing[:4]}{'...' if len(missing) > 4 else ''}")
+    for k, shp in exp.items():
+        if tuple(sd[k].shape) != tuple(shp):
+            raise RuntimeError(f"state_dict[{k}] has shape {tuple(sd[k].shape)}, expected {shp}")
