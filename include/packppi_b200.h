@@ -1,0 +1,123 @@
+/* libpackppi_b200.so - C ABI of the B200-native PackPPI-MSC sampling / PackPPI-Prox kernels.
+ *
+ * The reference (Jackz915/PackPPI) is pure Python on PyTorch and has no FFI; each entry point below replaces the
+ * Python function cited next to it (paths under the reference's src/).  A maintainer binds them with ctypes
+ * (INTEGRATION.md shows the stub): plain device pointers from tensor.data_ptr(), int64 sizes, and the CUDA stream
+ * from torch.cuda.current_stream().cuda_stream.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless marked host; fp32 unless the type says otherwise
+ *   - the caller owns all memory (inputs, outputs, workspaces); the library never allocates or frees
+ *   - calls are asynchronous and stream-ordered; no entry point synchronises with the host
+ *   - return value 0 = success; otherwise pp_last_error() (thread-local, host) describes the failure
+ *   - G = B*L residues of the padded batch, K = min(32, L) neighbours, S = diffusion samples that share the
+ *     backbone; per-sample arrays have S*G rows, row r = s*G + g
+ */
+#ifndef PACKPPI_B200_H
+#define PACKPPI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* pp_stream_t; /* cudaStream_t */
+
+int pp_abi_version(void);
+const char* pp_last_error(void);
+int pp_check_device(void); /* 0 iff the current device is compute capability 10.x */
+
+/* Packed weight blob (packppi_b200/csrc/weights_layout.h).  Entry i has a name, an offset and a size in floats;
+ * the host packs the reference state_dict (models/TorsionalDiffusion.py:39-68) by name. */
+int64_t pp_layout_count(void);
+int64_t pp_layout_total_floats(void);
+int pp_layout_entry(int64_t i, const char** name, int64_t* offset, int64_t* size);
+int64_t pp_geo_stride(void);   /* floats per residue geometry record */
+int64_t pp_table_stride(void); /* floats per residue-type table record */
+
+/* ProteinEncoder._dist (models/components/encoder.py:105-118) + mask_attend (models/components/mpnn.py:49-50).
+ * X [B][L][14][3], residue_mask [B][L] -> E_idx int64 [B][L][K] (index inside the complex, ascending distance,
+ * lowest index first among equal distances), nbr int32 [G][K] (row of the padded batch), D_neighbors [G][K] or
+ * NULL, mask_attend [G][K] or NULL, msum [G] = mean_k mask_attend or NULL. */
+int pp_knn_build(const float* X, const float* residue_mask, int64_t B, int64_t L, int64_t K, int64_t* E_idx,
+                 int32_t* nbr, float* D_neighbors, float* mask_attend, float* msum, pp_stream_t stream);
+
+/* Rigid.from_3_points(N,CA,C) (utils/rigid_utils.py:1126-1179, fixed=True) and _impute_CB (encoder.py:137-142).
+ * geo [G][pp_geo_stride()]: R(9, row-major) t(3) N CA C O CB(15). */
+int pp_geometry_build(const float* X, int64_t G, float* geo, pp_stream_t stream);
+
+/* Edge half of ProteinEncoder.forward (encoder.py:34-47,120-196,231-236,243-244): 468 features per edge,
+ * Linear(468,128), LayerNorm -> hE0 [G][K][128].  Step-invariant: call once per batch. */
+int pp_edge_embed(const float* weights, const float* geo, const int32_t* nbr, const int64_t* residue_index,
+                  const int64_t* chain_indices, int64_t G, int64_t K, float* hE0, pp_stream_t stream);
+
+/* Node half of ProteinEncoder.forward (encoder.py:217-229,239-242; layers.py:248-268) including the sin/cos of the
+ * noised chi (models/TorsionalDiffusion.py:91-92).  bb_sincos [G][6], chi [S*G][4], chi_mask [G][4]; or, when
+ * sc_sincos [S*G][8] is not NULL, the already masked sin/cos pairs as ProteinEncoder.forward receives them.
+ * t: one value (t_stride 0) or one per row (t_stride 1) -> hV [S*G][128]. */
+int pp_node_embed(const float* weights, const int64_t* residue_type, const float* bb_sincos, const float* chi,
+                  const float* chi_mask, const float* sc_sincos, const float* t, int64_t t_stride, int64_t G,
+                  int64_t S, float* hV, pp_stream_t stream);
+
+/* InvariantPointMessagePassing.forward (models/components/layers.py:119-148), layer = 0..2.  hV is updated in
+ * place; hE_in has G rows when he_shared != 0 (the step-invariant hE0) else S*G rows; hE_out [S*G][K][128] may
+ * alias hE_in when he_shared == 0; edge_update == 0 skips the edge half.
+ * Workspaces: wsA, wsN, wsAcc [S*G][128], wsP [S*G][24]. */
+int pp_ipmp_layer(const float* weights, int64_t layer, const float* geo, const int32_t* nbr,
+                  const float* mask_attend, const float* msum, const float* residue_mask, int64_t G, int64_t K,
+                  int64_t S, float* hV, const float* hE_in, int64_t he_shared, float* hE_out, int64_t edge_update,
+                  float* wsA, float* wsN, float* wsP, float* wsAcc, pp_stream_t stream);
+
+/* decoder_score (models/TorsionalDiffusion.py:62-68,106-108) and, if do_step, both SO2VESchedule.step calls in ode
+ * mode plus wrap and mask (models/components/schedule.py:198-235, TorsionalDiffusion.py:272-280):
+ *   chi <- wrap(chi + [step_mask] c_ode (score * w_anneal)) * chi_mask.
+ * score_out [S*G][4] or NULL; step_mask uint8 [G][4]; chi_mask [G][4]; chi [S*G][4] in/out. */
+int pp_decode_step(const float* weights, const float* hV, int64_t G, int64_t S, float* score_out, int64_t do_step,
+                   float c_ode, float w_anneal, const uint8_t* step_mask, const float* chi_mask, float* chi,
+                   pp_stream_t stream);
+
+/* get_atom14_coords (models/components/__init__.py:76-120).  tables [21][pp_table_stride()] from
+ * packppi_b200.tables.packed_geometry(); chi [S*G][4] -> xyz_out [S*G][14][3]. */
+int pp_atom14_fwd(const float* tables, const float* X, const int64_t* residue_type, const float* chi, int64_t G,
+                  int64_t S, float* xyz_out, pp_stream_t stream);
+
+/* Residue neighbour list of the clash term (no reference counterpart: clash.py:139-149 is dense).
+ * fill = 0: writes reach [G] and counts [G].  The caller builds start [G+1] = exclusive prefix sum of counts.
+ * fill = 1: writes list [start[G]] (ascending neighbour index).  cutoff = 2 * max radius - overlap tolerance. */
+int pp_clash_neighbours(const float* tables, const float* X, const int64_t* residue_type, const float* atom_exists,
+                        const int64_t* residue_index, int64_t B, int64_t L, float cutoff, int64_t fill, float* reach,
+                        int32_t* counts, const int64_t* start, int32_t* list, pp_stream_t stream);
+
+/* compute_residue_clash (models/components/clash.py:335-365) and its gradient.
+ * lower/upper [21][14][14] from make_atom14_dists_bounds (utils/residue_constants.py:809-869).
+ * mode 0: per_res [S*G].  mode 1: also grad_chi [S*G][4] = d(sum_r res_w[r] per_res[r]) / d chi (analytic).
+ * Workspaces: atoms4 [S*G][14][4], axes [S*G][4][6], bound [S*G]. */
+int pp_clash_fwd_bwd(const float* tables, const float* lower, const float* upper, const float* X,
+                     const int64_t* residue_type, const float* atom_exists, const int64_t* nbr_start,
+                     const int32_t* nbr_list, const float* chi, int64_t G, int64_t S, float tol, float max_cut,
+                     int64_t mode, const float* res_w, float* per_res, float* grad_chi, float* atoms4, float* axes,
+                     float* bound, pp_stream_t stream);
+
+/* proximal_optimizer (models/components/optimize.py:5-73), one complex (B = 1, S = 1).
+ * pp_prox_init: find_clash_mask + optimiser state.  mean_out[1] = mean per-residue loss.
+ * pp_prox_step: one Adam step; loss_out[0] = loss before the update (the value the reference appends to
+ * loss_list), loss_out[1] = mean per-residue clash; snapshot = where(mask, x_new, SC_D).
+ * step_size = lr / (1 - beta1^t), bc2_sqrt = sqrt(1 - beta2^t) as torch.optim.Adam computes them on the host. */
+int64_t pp_prox_partial_floats(int64_t R);
+int pp_prox_init(const float* tables, const float* lower, const float* upper, const float* X,
+                 const int64_t* residue_type, const float* atom_exists, const int64_t* nbr_start,
+                 const int32_t* nbr_list, const float* sc_d, int64_t G, float tol, float max_cut, uint8_t* mask,
+                 float* z, float* x, float* m, float* v, float* per_res, float* mean_out, float* atoms4, float* axes,
+                 float* bound, float* partial, pp_stream_t stream);
+int pp_prox_step(const float* tables, const float* lower, const float* upper, const float* X,
+                 const int64_t* residue_type, const float* atom_exists, const int64_t* nbr_start,
+                 const int32_t* nbr_list, const float* sc_d, const uint8_t* mask, const float* z, float* x, float* m,
+                 float* v, int64_t G, float tol, float max_cut, float lamda, float step_size, float bc2_sqrt,
+                 float beta1, float beta2, float eps, float* snapshot, float* loss_out, float* per_res, float* atoms4,
+                 float* axes, float* bound, float* partial, pp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

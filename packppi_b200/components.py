@@ -1,0 +1,99 @@
+"""Drop-in mirrors of the reference's free functions on the hot path, backed by libpackppi_b200.so.
+
+  get_atom14_coords(X, S, BB_D, SC_D)                       reference src/models/components/__init__.py:76-120
+  compute_residue_clash(batch, SC_D, vtf, cot, eps)         src/models/components/clash.py:335-365
+  find_clash_mask / proximal_optimizer                      src/models/components/optimize.py:5-73
+Same names, positional order and return types.  CUDA tensors only (RuntimeError otherwise: the reference
+remains the `--device cpu` path).  `compute_residue_clash` is differentiable in SC_D through an analytic
+backward kernel.
+"""
+import torch
+
+from . import _lib
+from .engine import ClashContext, DeviceTables
+
+
+def _cuda_only(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f"packppi_b200.{what}: CUDA tensors only, there is no CPU fallback "
+                           "(use the reference implementation for --device cpu)")
+
+
+def get_atom14_coords(X, S, BB_D, SC_D):
+    """chi angles -> atom14 coordinates [..., L, 14, 3].  BB_D is accepted for signature parity; the omega/phi/psi
+    frames only own slots that are overwritten with the input backbone, so it cannot influence the result.
+    Leading dimensions of SC_D beyond those of X are treated as samples of the same backbone."""
+    _cuda_only(X, "get_atom14_coords")
+    L = X.shape[-3]
+    G = X.numel() // 42
+    Xf = X.reshape(G, 14, 3).to(torch.float32).contiguous()
+    Sf = S.reshape(-1).to(torch.int64).contiguous()
+    chi = SC_D.reshape(-1, 4).to(torch.float32).contiguous()
+    if chi.shape[0] % G != 0:
+        raise RuntimeError("get_atom14_coords: SC_D does not match X")
+    n = chi.shape[0] // G
+    out = torch.empty(n * G, 14, 3, dtype=torch.float32, device=X.device)
+    _lib.call("pp_atom14_fwd", DeviceTables.get(X.device).geo, Xf, Sf, chi, G, n, out)
+    return out.reshape(*SC_D.shape[:-2], L, 14, 3)
+
+
+_ctx_cache = {}
+
+
+def clash_context(batch, violation_tolerance_factor=12., clash_overlap_tolerance=0.5):
+    """Static neighbour list / tables for `batch`, cached while the same tensors are passed again."""
+    key = (batch.X.data_ptr(), batch.atom_mask.data_ptr(), batch.residue_index.data_ptr(), tuple(batch.X.shape),
+           float(violation_tolerance_factor), float(clash_overlap_tolerance))
+    hit = _ctx_cache.get("ctx")
+    if hit is None or hit[0] != key:
+        ctx = ClashContext(batch.X.device, batch.X, batch.residue_type, batch.atom_mask, batch.residue_index,
+                           violation_tolerance_factor, clash_overlap_tolerance)
+        _ctx_cache["ctx"] = (key, ctx)
+    return _ctx_cache["ctx"][1]
+
+
+class _ResidueClash(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, SC_D, cc):
+        chi = SC_D.detach().reshape(-1, 4).to(torch.float32).contiguous()
+        per_res, _ = cc.evaluate(chi)
+        ctx.cc = cc
+        ctx.save_for_backward(chi)
+        ctx.in_shape = SC_D.shape
+        return per_res.reshape(SC_D.shape[:-1])
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (chi,) = ctx.saved_tensors
+        w = grad_out.reshape(-1).to(torch.float32).contiguous()
+        _, g = ctx.cc.evaluate(chi, res_w=w)
+        return g.reshape(ctx.in_shape), None
+
+
+def compute_residue_clash(batch, SC_D, violation_tolerance_factor=12., clash_overlap_tolerance=0.5, eps=1e-10):
+    """Per-residue structural-violation loss [B, L] of the side chains rebuilt from SC_D (clash.py:335-365)."""
+    _cuda_only(SC_D, "compute_residue_clash")
+    if eps != 1e-10:
+        raise NotImplementedError("compute_residue_clash: eps is fixed to the reference default 1e-10")
+    cc = clash_context(batch, violation_tolerance_factor, clash_overlap_tolerance)
+    return _ResidueClash.apply(SC_D, cc)
+
+
+def find_clash_mask(batch, SC_D, violation_tolerance_factor, clash_overlap_tolerance):
+    """optimize.py:5-18: residues whose loss exceeds the mean, expanded to the four chi -> bool [B, L, 4]."""
+    per = compute_residue_clash(batch, SC_D.detach(), violation_tolerance_factor, clash_overlap_tolerance)
+    return (per > per.mean()).unsqueeze(-1).expand(-1, -1, 4)
+
+
+def proximal_optimizer(batch, SC_D, violation_tolerance_factor, clash_overlap_tolerance, lamda, num_steps=50):
+    """optimize.py:21-73 -> (list of num_steps tensors [1, L, 4], list of num_steps floats).
+
+    The whole loop (rebuild, loss, analytic gradient, Adam, snapshot) runs on the device; the losses are copied
+    to the host once at the end instead of one `.item()` per step."""
+    assert batch.num_proteins == 1
+    _cuda_only(SC_D, "proximal_optimizer")
+    cc = clash_context(batch, violation_tolerance_factor, clash_overlap_tolerance)
+    L = SC_D.shape[-2]
+    snaps, losses, _ = cc.proximal(SC_D.detach().reshape(-1, 4).to(torch.float32), float(lamda), int(num_steps))
+    loss_list = losses.cpu().tolist()
+    return [snaps[k].reshape(1, L, 4) for k in range(num_steps)], loss_list

@@ -1,0 +1,90 @@
+// Score decoder fused with the reverse-ODE update of the chi angles.
+//
+// Replaces decoder_score (reference src/models/TorsionalDiffusion.py:62-68,106-108: Linear 128-64 relu 64-32, ReLU,
+// 32-16 relu 16-4) and, when `do_step` is set, the two SO2VESchedule.step calls plus the wrap and mask of the
+// sampling loop (schedule.py:198-235 ode branch, TorsionalDiffusion.py:272-280):
+//     chi <- wrap(chi + [step_mask] * c * (score * w)) * SC_D_mask ,  wrap(x) = (x + pi) mod 2pi - pi
+// with c = 0.5 g(t)^2 dt and w = annealed weight, both evaluated on the host in fp32 exactly as the reference's
+// 0-dim tensor arithmetic does, so the kernel only multiplies.
+#include "common.cuh"
+#include "weights_layout.h"
+
+namespace pp {
+
+// one warp per residue row; activations are exchanged through shuffles
+__global__ void decode_step_kernel(const float* __restrict__ W, const float* __restrict__ hV, int G, int S,
+                                   float* __restrict__ score_out, int do_step, float c_ode, float w_anneal,
+                                   const unsigned char* __restrict__ step_mask /*[G][4]*/,
+                                   const float* __restrict__ chi_mask /*[G][4]*/, float* __restrict__ chi /*[R][4]*/) {
+  int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (r >= S * G) return;
+  const float* W0 = W + PP_OFF(DEC_W0);
+  const float* W1 = W + PP_OFF(DEC_W1);
+  const float* W2 = W + PP_OFF(DEC_W2);
+  const float* W3 = W + PP_OFF(DEC_W3);
+  float4 h = *reinterpret_cast<const float4*>(hV + (size_t)r * 128 + lane * 4);  // inputs lane*4 .. lane*4+3
+
+  // 128 -> 64 : lane owns outputs 2*lane, 2*lane+1
+  float2 a0 = *reinterpret_cast<const float2*>(W + PP_OFF(DEC_B0) + lane * 2);
+#pragma unroll 4
+  for (int src = 0; src < 32; ++src) {
+    float x = __shfl_sync(0xffffffffu, h.x, src), y = __shfl_sync(0xffffffffu, h.y, src);
+    float z = __shfl_sync(0xffffffffu, h.z, src), w = __shfl_sync(0xffffffffu, h.w, src);
+    const float* wr = W0 + (size_t)(src * 4) * 64 + lane * 2;
+    float2 w0 = *reinterpret_cast<const float2*>(wr), w1 = *reinterpret_cast<const float2*>(wr + 64);
+    float2 w2 = *reinterpret_cast<const float2*>(wr + 128), w3 = *reinterpret_cast<const float2*>(wr + 192);
+    a0.x = fmaf(x, w0.x, a0.x); a0.y = fmaf(x, w0.y, a0.y);
+    a0.x = fmaf(y, w1.x, a0.x); a0.y = fmaf(y, w1.y, a0.y);
+    a0.x = fmaf(z, w2.x, a0.x); a0.y = fmaf(z, w2.y, a0.y);
+    a0.x = fmaf(w, w3.x, a0.x); a0.y = fmaf(w, w3.y, a0.y);
+  }
+  a0.x = fmaxf(a0.x, 0.f);
+  a0.y = fmaxf(a0.y, 0.f);
+  // 64 -> 32 : lane owns output lane; then the nn.ReLU between the two MLPs
+  float a1 = W[PP_OFF(DEC_B1) + lane];
+#pragma unroll 8
+  for (int src = 0; src < 32; ++src) {
+    float x = __shfl_sync(0xffffffffu, a0.x, src), y = __shfl_sync(0xffffffffu, a0.y, src);
+    a1 = fmaf(x, W1[(size_t)(src * 2) * 32 + lane], a1);
+    a1 = fmaf(y, W1[(size_t)(src * 2 + 1) * 32 + lane], a1);
+  }
+  a1 = fmaxf(a1, 0.f);
+  // 32 -> 16 (relu) : lanes 0..15
+  float a2 = W[PP_OFF(DEC_B2) + (lane & 15)];
+#pragma unroll 8
+  for (int src = 0; src < 32; ++src) a2 = fmaf(__shfl_sync(0xffffffffu, a1, src), W2[src * 16 + (lane & 15)], a2);
+  a2 = fmaxf(a2, 0.f);
+  // 16 -> 4 : lanes 0..3
+  float a3 = W[PP_OFF(DEC_B3) + (lane & 3)];
+#pragma unroll
+  for (int src = 0; src < 16; ++src) a3 = fmaf(__shfl_sync(0xffffffffu, a2, src), W3[src * 4 + (lane & 3)], a3);
+
+  if (lane < 4) {
+    size_t o = (size_t)r * 4 + lane;
+    if (score_out) score_out[o] = a3;
+    if (do_step) {
+      int g = r % G;
+      float x = chi[o];
+      if (step_mask[(size_t)g * 4 + lane]) x = __fadd_rn(x, __fmul_rn(c_ode, __fmul_rn(a3, w_anneal)));
+      float y = fmodf(__fadd_rn(x, PP_PI_F), PP_TWO_PI_F);
+      if (y != 0.f && y < 0.f) y = __fadd_rn(y, PP_TWO_PI_F);  // python-style remainder (torch %)
+      chi[o] = __fmul_rn(__fsub_rn(y, PP_PI_F), chi_mask[(size_t)g * 4 + lane]);
+    }
+  }
+}
+
+}  // namespace pp
+
+extern "C" int pp_decode_step(const float* weights, const float* hV, int64_t G, int64_t S, float* score_out,
+                              int64_t do_step, float c_ode, float w_anneal, const uint8_t* step_mask,
+                              const float* chi_mask, float* chi, cudaStream_t stream) {
+  PP_REQUIRE(weights && hV, "null pointer");
+  PP_REQUIRE(G > 0 && S > 0, "bad sizes");
+  PP_REQUIRE(score_out || do_step, "nothing to do");
+  PP_REQUIRE(!do_step || (step_mask && chi_mask && chi), "step needs step_mask, chi_mask and chi");
+  long long R = S * G;
+  pp::decode_step_kernel<<<(unsigned)((R * 32 + 255) / 256), 256, 0, stream>>>(
+      weights, hV, (int)G, (int)S, score_out, (int)do_step, c_ode, w_anneal, step_mask, chi_mask, chi);
+  return pp::check_launch("pp_decode_step");
+}

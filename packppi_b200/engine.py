@@ -1,0 +1,274 @@
+"""Host-side orchestration of the kernels: buffers, launch order, per-step scalars.  PyTorch is used for device
+memory and streams only; every arithmetic step of the hot path is a kernel of libpackppi_b200.so.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, tables
+from .weights import pack_weights
+
+SIGMA_MIN, SIGMA_MAX = 0.01 * np.pi, np.pi  # schedule.py:148-149 defaults
+TOP_K = 32
+
+
+def _f32(t, dev):
+    return t.to(device=dev, dtype=torch.float32).contiguous()
+
+
+def _i64(t, dev):
+    return t.to(device=dev, dtype=torch.int64).contiguous()
+
+
+class DeviceTables:
+    """Per-device chemistry tables (uploaded once, cached)."""
+    _cache = {}
+
+    @classmethod
+    def get(cls, dev):
+        key = (dev.type, dev.index)
+        if key not in cls._cache:
+            cls._cache[key] = cls(dev)
+        return cls._cache[key]
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.geo = torch.from_numpy(tables.packed_geometry()).to(dev).contiguous()
+        assert self.geo.shape[1] == _lib.load().pp_table_stride()
+        self._bounds = {}
+        self.max_radius = float(tables.raw()["clash_radius"].max())
+
+    def bounds(self, cot, vtf):
+        key = (float(cot), float(vtf))
+        if key not in self._bounds:
+            lo, hi = tables.dist_bounds(cot, vtf)
+            self._bounds[key] = (torch.from_numpy(lo).to(self.dev).contiguous(),
+                                 torch.from_numpy(hi).to(self.dev).contiguous())
+        return self._bounds[key]
+
+
+class Graph:
+    """Step-invariant state of one padded batch: neighbour lists, geometry records,
+    attention mask and, once `edge_embed` ran, the embedded edge features h_E0."""
+
+    def __init__(self, X, residue_mask, top_k=TOP_K):
+        dev = X.device
+        self.B, self.L = int(X.shape[0]), int(X.shape[1])
+        self.G = self.B * self.L
+        self.K = min(top_k, self.L)
+        self.X = _f32(X, dev)
+        self.mask = _f32(residue_mask, dev)
+        G, K = self.G, self.K
+        self.E_idx = torch.empty(self.B, self.L, K, dtype=torch.int64, device=dev)
+        self.nbr = torch.empty(G, K, dtype=torch.int32, device=dev)
+        self.D_neighbors = torch.empty(self.B, self.L, K, dtype=torch.float32, device=dev)
+        self.mask_attend = torch.empty(G, K, dtype=torch.float32, device=dev)
+        self.msum = torch.empty(G, dtype=torch.float32, device=dev)
+        self.geo = torch.empty(G, _lib.load().pp_geo_stride(), dtype=torch.float32, device=dev)
+        _lib.call("pp_knn_build", self.X, self.mask, self.B, self.L, K, self.E_idx, self.nbr, self.D_neighbors,
+                  self.mask_attend, self.msum)
+        _lib.call("pp_geometry_build", self.X, G, self.geo)
+        self.hE0 = None
+
+    def edge_embed(self, wblob, residue_index, chain_indices):
+        dev = self.X.device
+        self.hE0 = torch.empty(self.G, self.K, 128, dtype=torch.float32, device=dev)
+        _lib.call("pp_edge_embed", wblob, self.geo, self.nbr, _i64(residue_index, dev), _i64(chain_indices, dev),
+                  self.G, self.K, self.hE0)
+        return self.hE0
+
+
+class Workspace:
+    """Per-sample activations and scratch for S*G residue rows."""
+
+    def __init__(self, G, K, S, dev):
+        R = S * G
+        z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)  # noqa: E731
+        self.G, self.K, self.S = G, K, S
+        self.hV = z(R, 128)
+        self.hE = z(R, K, 128)
+        self.wsA, self.wsN, self.wsAcc = z(R, 128), z(R, 128), z(R, 128)
+        self.wsP = z(R, 24)
+        self.score = z(R, 4)
+
+
+class Engine:
+    """Packed weights + kernels for one device."""
+
+    def __init__(self, state_dict, device):
+        self.dev = torch.device(device)
+        if self.dev.type != "cuda":
+            raise RuntimeError("packppi_b200 runs on CUDA devices only; there is no CPU fallback "
+                               "(use the reference implementation for --device cpu)")
+        layout, total = _lib.layout()
+        self.wblob = pack_weights(state_dict, layout, total).to(self.dev)
+        self.tables = DeviceTables.get(self.dev)
+        self._ws = {}
+
+    # ------------------------------------------------------------------ graph
+    def build_graph(self, batch, with_edges=True):
+        g = Graph(batch.X.to(self.dev), batch.residue_mask.to(self.dev))
+        if with_edges:
+            g.edge_embed(self.wblob, batch.residue_index, batch.chain_indices)
+        return g
+
+    def workspace(self, G, K, S):
+        key = (G, K, S)
+        if key not in self._ws:
+            self._ws.clear()  # one live shape at a time keeps memory bounded
+            self._ws[key] = Workspace(G, K, S, self.dev)
+        return self._ws[key]
+
+    # ------------------------------------------------------------------ network
+    def node_inputs(self, batch):
+        dev = self.dev
+        return dict(rtype=_i64(batch.residue_type.reshape(-1), dev),
+                    bb=_f32(batch.BB_D_sincos.reshape(-1, 6), dev),
+                    chi_mask=_f32(batch.SC_D_mask.reshape(-1, 4), dev))
+
+    def forward_layers(self, graph, ws, ni, chi, t, t_stride, hE0=None, sc_sincos=None):
+        """node embedding + 3 IPMP layers on ws (rows S*G); leaves h_V in ws.hV."""
+        G, K, S = graph.G, graph.K, ws.S
+        W = self.wblob
+        _lib.call("pp_node_embed", W, ni["rtype"], ni["bb"], chi, ni["chi_mask"], sc_sincos, t, t_stride, G, S, ws.hV)
+        hE0 = graph.hE0 if hE0 is None else hE0
+        for layer in range(3):
+            first = layer == 0
+            _lib.call("pp_ipmp_layer", W, layer, graph.geo, graph.nbr, graph.mask_attend, graph.msum, graph.mask, G, K,
+                      S, ws.hV, hE0 if first else ws.hE, 1 if first else 0, ws.hE, 1 if layer < 2 else 0, ws.wsA,
+                      ws.wsN, ws.wsP, ws.wsAcc)
+        return ws.hV
+
+    def network(self, graph, batch, chi, t):
+        """chi [S*G,4] (device), t [S*G] -> (score [S*G,4], h_V [S*G,128])  (TorsionalDiffusion.py:90-109)."""
+        S = chi.shape[0] // graph.G
+        ws = self.workspace(graph.G, graph.K, S)
+        ni = self.node_inputs(batch)
+        self.forward_layers(graph, ws, ni, chi, t, 1)
+        _lib.call("pp_decode_step", self.wblob, ws.hV, graph.G, S, ws.score, 0, 0.0, 0.0, None, None, None)
+        return ws.score, ws.hV
+
+    # ------------------------------------------------------------------ sampling
+    @staticmethod
+    def ode_coefficients(n_steps=30, annealed_temp=3.0):
+        """Per-step (t, c = 0.5 g^2 dt, w) with the reference's fp32 tensor arithmetic (schedule.py:165-235,286-288,
+        TorsionalDiffusion.py:259-263): the schedule entries are 0-dim fp32 tensors, the numpy scalars fold in."""
+        sched = torch.linspace(1, 0, n_steps + 1)
+        lo, hi = np.log(SIGMA_MIN), np.log(SIGMA_MAX)
+        out = []
+        for j in range(n_steps):
+            time, dt = sched[j], sched[j] - sched[j + 1]
+            sigma = torch.exp(lo + (hi - lo) * time)
+            g = sigma * np.sqrt(2 * np.log(SIGMA_MAX / SIGMA_MIN))
+            if annealed_temp:
+                alpha = 1 - (sigma / np.exp(hi)) ** 2
+                w = annealed_temp / (alpha + (1 - alpha) * annealed_temp)
+            else:
+                w = torch.tensor(1.0)
+            c = 0.5 * g ** 2 * dt
+            out.append((float(time), float(c), float(w)))
+        return out
+
+    def sample(self, graph, batch, chi_init, n_steps=30, annealed_temp=3.0, trajectory=None):
+        """Reverse-ODE loop (TorsionalDiffusion.py:259-280) on S samples that share `graph`.
+
+        chi_init [S*G,4] on the device; returns the final chi [S*G,4] (a new tensor)."""
+        G, K = graph.G, graph.K
+        S = chi_init.shape[0] // G
+        ws = self.workspace(G, K, S)
+        ni = self.node_inputs(batch)
+        step_mask = (batch.chi_1pi_periodic_mask.to(self.dev).reshape(-1, 4).bool() |
+                     batch.chi_2pi_periodic_mask.to(self.dev).reshape(-1, 4).bool()).to(torch.uint8).contiguous()
+        chi = chi_init.clone().contiguous()
+        tbuf = torch.empty(1, dtype=torch.float32, device=self.dev)
+        coefs = self.ode_coefficients(n_steps, annealed_temp)
+        tvals = torch.tensor([c[0] for c in coefs], dtype=torch.float32, device=self.dev)
+        for j, (_, c, w) in enumerate(coefs):
+            tbuf = tvals[j:j + 1]
+            self.forward_layers(graph, ws, ni, chi, tbuf, 0)
+            _lib.call("pp_decode_step", self.wblob, ws.hV, G, S, None, 1, c, w, step_mask, ni["chi_mask"], chi)
+            if trajectory is not None:
+                trajectory.append(chi.clone())
+        return chi
+
+    # ------------------------------------------------------------------ atom14 / clash / proximal
+    def atom14(self, X, residue_type, chi):
+        """X [G,14,3], residue_type [G], chi [S*G,4] -> [S*G,14,3]."""
+        G = X.shape[0]
+        S = chi.shape[0] // G
+        out = torch.empty(S * G, 14, 3, dtype=torch.float32, device=self.dev)
+        _lib.call("pp_atom14_fwd", self.tables.geo, X, residue_type, chi, G, S, out)
+        return out
+
+
+class ClashContext:
+    """Static part of the clash term for one padded batch: tables, bounds, residue neighbour list."""
+
+    def __init__(self, dev, X, residue_type, atom_mask, residue_index, vtf=12.0, cot=0.5):
+        self.dev = dev
+        self.tables = DeviceTables.get(dev)
+        self.B, self.L = int(X.shape[0]), int(X.shape[1])
+        self.G = self.B * self.L
+        self.X = _f32(X.reshape(self.G, 14, 3), dev)
+        self.rtype = _i64(residue_type.reshape(-1), dev)
+        self.exists = _f32(atom_mask.reshape(self.G, 14), dev)
+        self.ridx = _i64(residue_index.reshape(-1), dev)
+        self.tol = float(cot)
+        self.lower, self.upper = self.tables.bounds(cot, vtf)
+        self.max_cut = max(2.0 * self.tables.max_radius - float(cot), 0.0)
+        G = self.G
+        self.reach = torch.empty(G, dtype=torch.float32, device=dev)
+        counts = torch.empty(G, dtype=torch.int32, device=dev)
+        args = (self.tables.geo, self.X, self.rtype, self.exists, self.ridx, self.B, self.L, self.max_cut)
+        _lib.call("pp_clash_neighbours", *args, 0, self.reach, counts, None, None)
+        self.start = torch.zeros(G + 1, dtype=torch.int64, device=dev)
+        self.start[1:] = torch.cumsum(counts.to(torch.int64), 0)
+        total = int(self.start[-1].item())  # one host sync per complex, not per step
+        self.list = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        _lib.call("pp_clash_neighbours", *args, 1, self.reach, None, self.start, self.list)
+        self._ws = {}
+
+    def scratch(self, S):
+        if S not in self._ws:
+            R = S * self.G
+            z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=self.dev)  # noqa: E731
+            self._ws[S] = dict(atoms4=z(R, 14, 4), axes=z(R, 4, 6), bound=z(R))
+        return self._ws[S]
+
+    def evaluate(self, chi, res_w=None):
+        """chi [S*G,4] -> per_res [S*G] (and grad [S*G,4] of sum_r res_w[r]*per_res[r] when res_w is given)."""
+        S = chi.shape[0] // self.G
+        ws = self.scratch(S)
+        per_res = torch.empty(S * self.G, dtype=torch.float32, device=self.dev)
+        grad = torch.empty(S * self.G, 4, dtype=torch.float32, device=self.dev) if res_w is not None else None
+        _lib.call("pp_clash_fwd_bwd", self.tables.geo, self.lower, self.upper, self.X, self.rtype, self.exists,
+                  self.start, self.list, chi, self.G, S, self.tol, self.max_cut, 0 if res_w is None else 1, res_w,
+                  per_res, grad, ws["atoms4"], ws["axes"], ws["bound"])
+        return per_res, grad
+
+    def proximal(self, sc_d, lamda, num_steps, lr=1e-2, beta1=0.9, beta2=0.999, eps=1e-8):
+        """optimize.py:21-73 for one complex.  Returns (snapshots [num_steps,G,4], losses [num_steps], mask [G,4]);
+        everything stays on the device, the caller decides when to synchronise."""
+        assert self.B == 1
+        G, dev = self.G, self.dev
+        ws = self.scratch(1)
+        f = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)  # noqa: E731
+        mask = torch.zeros(G, 4, dtype=torch.uint8, device=dev)
+        z, x, m, v = f(G, 4), f(G, 4), f(G, 4), f(G, 4)
+        per_res, mean = f(G), f(2)
+        partial = f(int(_lib.load().pp_prox_partial_floats(G)))
+        snaps = f(num_steps, G, 4)
+        losses = f(num_steps, 2)
+        sc_d = sc_d.contiguous()
+        static = (self.tables.geo, self.lower, self.upper, self.X, self.rtype, self.exists, self.start, self.list, sc_d)
+        _lib.call("pp_prox_init", *static, G, self.tol, self.max_cut, mask, z, x, m, v, per_res, mean, ws["atoms4"],
+                  ws["axes"], ws["bound"], partial)
+        for k in range(num_steps):
+            t = k + 1
+            step_size = lr / (1 - beta1 ** t)  # torch.optim.Adam, single-tensor path
+            bc2_sqrt = math.sqrt(1 - beta2 ** t)
+            _lib.call("pp_prox_step", *static, mask, z, x, m, v, G, self.tol, self.max_cut, float(lamda), step_size,
+                      bc2_sqrt, beta1, beta2, eps, snaps[k], losses[k], per_res, ws["atoms4"], ws["axes"], ws["bound"],
+                      partial)
+        return snaps, losses[:, 0], mask

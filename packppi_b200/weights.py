@@ -89,3 +89,65 @@ def check_state_dict(sd):
     for k, shp in exp.items():
         if tuple(sd[k].shape) != tuple(shp):
             raise RuntimeError(f"state_dict[{k}] has shape {tuple(sd[k].shape)}, expected {shp}")
+
+
+def pack_weights(sd, layout, total_floats):
+    """state_dict -> the flat fp32 blob the kernels read (layout from `_lib.layout()`, documented in
+    csrc/weights_layout.h).  Runs on the host; the caller moves the result to the device."""
+    check_state_dict(sd)
+    f = {k: v.detach().to("cpu", torch.float32) for k, v in sd.items()}
+    blob = torch.zeros(total_floats, dtype=torch.float32)
+
+    def put(name, t):
+        off, size = layout[name]
+        t = t.contiguous().reshape(-1)
+        assert t.numel() <= size, (name, t.numel(), size)
+        blob[off:off + t.numel()] = t
+
+    put("ENC_NODE_WT", f["encoder.node_embedding.weight"].t())
+    put("ENC_NODE_B", f["encoder.node_embedding.bias"])
+    put("ENC_NODE_LNG", f["encoder.norm_nodes.weight"])
+    put("ENC_NODE_LNB", f["encoder.norm_nodes.bias"])
+    We = f["encoder.edge_embedding.weight"]  # [128, 468] = [relpos 65 | rbf 400 | type | phi psi]
+    Wt = torch.zeros(496, H)
+    Wt[0:400] = We[:, 65:465].t()
+    Wt[400:465] = We[:, 0:65].t()
+    Wt[480:483] = We[:, 465:468].t()
+    put("ENC_EDGE_WT", Wt)
+    put("ENC_EDGE_B", f["encoder.edge_embedding.bias"])
+    put("ENC_EDGE_LNG", f["encoder.norm_edges.weight"])
+    put("ENC_EDGE_LNB", f["encoder.norm_edges.bias"])
+    for l in range(N_LAYERS):
+        p = f"mpnn.mpnn_layers.{l}."
+        for tag, pts, fn in (("N", "points_fn_node", "node_message_fn"), ("E", "points_fn_edge", "edge_message_fn")):
+            q = f"L{l}_{tag}_"
+            Win = f[p + fn + ".W_in.weight"]  # [128, 456]
+            put(q + "WP", f[p + pts + ".weight"].t())
+            put(q + "BP", f[p + pts + ".bias"])
+            put(q + "WAG", torch.cat([Win[:, 0:128].t(), Win[:, 384:416].t()], 0))
+            put(q + "B1", f[p + fn + ".W_in.bias"])
+            put(q + "WN", Win[:, 256:384].t())
+            put(q + "WEG", torch.cat([Win[:, 128:256].t(), Win[:, 416:456].t()], 0))
+            put(q + "W2", f[p + fn + ".W_inter.0.weight"].t())
+            put(q + "B2", f[p + fn + ".W_inter.0.bias"])
+            put(q + "W3", f[p + fn + ".W_out.weight"].t())
+            put(q + "B3", f[p + fn + ".W_out.bias"])
+        for i in range(4):
+            put(f"L{l}_LN{i}_G", f[p + f"norm.{i}.weight"])
+            put(f"L{l}_LN{i}_B", f[p + f"norm.{i}.bias"])
+        for tag, fn in (("NF", "node_dense"), ("EF", "edge_dense")):
+            put(f"L{l}_{tag}_WIN", f[p + fn + ".W_in.weight"].t())
+            put(f"L{l}_{tag}_BIN", f[p + fn + ".W_in.bias"])
+            put(f"L{l}_{tag}_WOUT", f[p + fn + ".W_out.weight"].t())
+            put(f"L{l}_{tag}_BOUT", f[p + fn + ".W_out.bias"])
+    put("DEC_W0", f["decoder_score.0.W_in.weight"].t())
+    put("DEC_B0", f["decoder_score.0.W_in.bias"])
+    put("DEC_W1", f["decoder_score.0.W_out.weight"].t())
+    put("DEC_B1", f["decoder_score.0.W_out.bias"])
+    put("DEC_W2", f["decoder_score.2.W_in.weight"].t())
+    put("DEC_B2", f["decoder_score.2.W_in.bias"])
+    put("DEC_W3", f["decoder_score.2.W_out.weight"].t())
+    put("DEC_B3", f["decoder_score.2.W_out.bias"])
+    put("RBF_MU", torch.linspace(0.0, 20.0, 16))  # encoder.py:122-123
+    put("TIME_FREQ", torch.exp(torch.arange(8, dtype=torch.float32) * -(math.log(10000) / 7)))  # layers.py:260-262
+    return blob
