@@ -69,6 +69,24 @@ int pp_ipmp_layer(const float* weights, int64_t layer, const float* geo, const i
                   int64_t S, float* hV, const float* hE_in, int64_t he_shared, float* hE_out, int64_t edge_update,
                   float* wsA, float* wsN, float* wsP, float* wsAcc, pp_stream_t stream);
 
+/* The four kernels of pp_ipmp_layer as separate entry points (same meaning of the arguments), for callers that
+ * time or re-order them: per-residue prologue (IPMP points, hoisted h_V_i / h_V_j products; path 0 = node message,
+ * 1 = edge message), per-edge node message + masked sum, per-residue node epilogue, per-edge edge update. */
+int pp_ipmp_node_pre(const float* weights, int64_t layer, int64_t path, const float* geo, const int32_t* nbr,
+                     const float* mask_attend, const float* residue_mask, int64_t G, int64_t K, int64_t S,
+                     const float* hV, float* wsA, float* wsN, float* wsP, pp_stream_t stream);
+int pp_ipmp_edge_node(const float* weights, int64_t layer, const float* geo, const int32_t* nbr,
+                      const float* mask_attend, const float* residue_mask, int64_t G, int64_t K, int64_t S,
+                      const float* hE_in, int64_t he_shared, const float* wsA, const float* wsN, const float* wsP,
+                      float* wsAcc, pp_stream_t stream);
+int pp_ipmp_node_post(const float* weights, int64_t layer, const float* geo, const int32_t* nbr,
+                      const float* mask_attend, const float* msum, const float* residue_mask, int64_t G, int64_t K,
+                      int64_t S, const float* wsAcc, float* hV, pp_stream_t stream);
+int pp_ipmp_edge_edge(const float* weights, int64_t layer, const float* geo, const int32_t* nbr,
+                      const float* mask_attend, const float* residue_mask, int64_t G, int64_t K, int64_t S,
+                      const float* hE_in, int64_t he_shared, const float* wsA, const float* wsN, const float* wsP,
+                      float* hE_out, pp_stream_t stream);
+
 /* decoder_score (models/TorsionalDiffusion.py:62-68,106-108) and, if do_step, both SO2VESchedule.step calls in ode
  * mode plus wrap and mask (models/components/schedule.py:198-235, TorsionalDiffusion.py:272-280):
  *   chi <- wrap(chi + [step_mask] c_ode (score * w_anneal)) * chi_mask.

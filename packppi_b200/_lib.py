@@ -21,6 +21,10 @@ SIGNATURES = {
     "pp_edge_embed": "ppppp" "ii" "p" "s",
     "pp_node_embed": "ppppppp" "iii" "p" "s",
     "pp_ipmp_layer": "p" "i" "ppppp" "iii" "pp" "i" "p" "i" "pppp" "s",
+    "pp_ipmp_node_pre": "p" "ii" "pppp" "iii" "pppp" "s",
+    "pp_ipmp_edge_node": "p" "i" "pppp" "iii" "p" "i" "pppp" "s",
+    "pp_ipmp_node_post": "p" "i" "ppppp" "iii" "pp" "s",
+    "pp_ipmp_edge_edge": "p" "i" "pppp" "iii" "p" "i" "pppp" "s",
     "pp_decode_step": "pp" "ii" "p" "i" "ff" "ppp" "s",
     "pp_atom14_fwd": "pppp" "ii" "p" "s",
     "pp_clash_neighbours": "ppppp" "ii" "f" "i" "pppp" "s",
@@ -31,6 +35,14 @@ SIGNATURES = {
 
 _KIND = {"p": _P, "i": _I, "f": _F, "s": _P}
 _lib = None
+
+# kernels launched per entry point (pp_ipmp_layer: 3, or 5 with the edge update - the caller passes `kernels=`)
+KERNELS = {"pp_knn_build": 1, "pp_geometry_build": 1, "pp_edge_embed": 1, "pp_node_embed": 1, "pp_ipmp_layer": 5,
+           "pp_ipmp_node_pre": 1, "pp_ipmp_edge_node": 1, "pp_ipmp_node_post": 1, "pp_ipmp_edge_edge": 1,
+           "pp_decode_step": 1, "pp_atom14_fwd": 1, "pp_clash_neighbours": 1, "pp_clash_fwd_bwd": 2,
+           "pp_prox_init": 4, "pp_prox_step": 3}
+LAUNCHES = 0      # running count of kernels launched through call()
+PROFILE = None    # {entry name: []} -> call() appends (start event, end event, rows) around those entries
 
 
 def load():
@@ -93,8 +105,9 @@ def ptr(t):
     return t.data_ptr()
 
 
-def call(name, *args, device=None):
+def call(name, *args, device=None, kernels=None, rows=0):
     """Invoke an entry point on torch's current stream; tensors are passed as device pointers."""
+    global LAUNCHES
     lib = load()
     dev = device
     conv = []
@@ -109,7 +122,15 @@ def call(name, *args, device=None):
         raise RuntimeError(f"{name}: no tensor argument to take the device from")
     _check_device(lib, dev.index if dev.index is not None else torch.cuda.current_device())
     with torch.cuda.device(dev):
-        stream = torch.cuda.current_stream().cuda_stream
-        rc = getattr(lib, name)(*conv, stream)
+        cur = torch.cuda.current_stream()
+        prof = PROFILE.get(name) if PROFILE is not None else None
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(cur)
+        rc = getattr(lib, name)(*conv, cur.cuda_stream)
+        if prof is not None:
+            e1.record(cur)
+            prof.append((e0, e1, rows))
+    LAUNCHES += KERNELS[name] if kernels is None else kernels
     if rc != 0:
         raise RuntimeError(f"{name} failed: {lib.pp_last_error().decode()}")

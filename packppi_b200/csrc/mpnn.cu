@@ -145,7 +145,7 @@ node_pre_kernel(MpnnCtx cx, PathWeights w, const float* __restrict__ hV, float* 
 // Returns x2 = relu(W2 relu(A_i + N_j + W_eg [h_E | pair]) + b2) in registers.  B0[:, 0:128] still holds h_E.
 // Returns false (uniformly) if every residue of the tile is masked; nothing has been computed then.
 __device__ __forceinline__ bool edge_front(float (&x2)[8][8], Smem& sm, const MpnnCtx& cx, const PathWeights& w,
-                                           const float* __restrict__ hE_in, int he_shared,
+                                           const float* hE_in, int he_shared,
                                            const float* __restrict__ A, const float* __restrict__ Nn,
                                            const float* __restrict__ pglob) {
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -305,7 +305,7 @@ struct NodePostWeights {
 
 __global__ void __launch_bounds__(kThreads, 1)
 node_post_kernel(MpnnCtx cx, NodePostWeights w, const float* __restrict__ accsum, const float* __restrict__ msum,
-                 const float* __restrict__ hV_in, float* __restrict__ hV_out) {
+                 const float* hV_in, float* hV_out /* may alias hV_in: a tile reads only the rows it writes */) {
   extern __shared__ __align__(16) float smem_raw[];
   Smem sm(smem_raw);
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -364,9 +364,9 @@ struct EdgePostWeights {
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
-edge_edge_kernel(MpnnCtx cx, PathWeights w, EdgePostWeights pw, const float* __restrict__ hE_in, int he_shared,
+edge_edge_kernel(MpnnCtx cx, PathWeights w, EdgePostWeights pw, const float* hE_in, int he_shared,
                  const float* __restrict__ A, const float* __restrict__ Nn, const float* __restrict__ pglob,
-                 float* __restrict__ hE_out) {
+                 float* hE_out /* may alias hE_in (he_shared == 0): a tile reads only the rows it writes */) {
   extern __shared__ __align__(16) float smem_raw[];
   Smem sm(smem_raw);
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -451,6 +451,72 @@ static int opt_in_smem(KernelT k) {
 
 using namespace pp;
 
+namespace {
+
+struct LayerArgs {
+  const float* weights;
+  int layer;
+  MpnnCtx cx;
+  unsigned row_tiles, edge_tiles;
+  const float* Lb;
+};
+
+int make_args(LayerArgs& a, const float* weights, int64_t layer, const float* geo, const int32_t* nbr,
+              const float* mask_attend, const float* residue_mask, int64_t G, int64_t K, int64_t S) {
+  PP_REQUIRE(weights && geo && nbr && mask_attend && residue_mask, "null pointer");
+  PP_REQUIRE(layer >= 0 && layer < 3, "layer out of range");
+  PP_REQUIRE(G > 0 && S > 0 && K > 0 && K <= PP_KMAX, "bad sizes");
+  PP_REQUIRE(S * G < (1ll << 31) / 128, "too many rows");
+  a.weights = weights;
+  a.layer = (int)layer;
+  a.cx = MpnnCtx{geo, nbr, mask_attend, residue_mask, (int)G, (int)K, (int)S};
+  const long long R = S * G;
+  a.row_tiles = (unsigned)((R + kTileRows - 1) / kTileRows);
+  a.edge_tiles = (unsigned)((R + 3) / 4);
+  a.Lb = weights + layer * wl::kLayerStride;
+  return 0;
+}
+
+int launch_node_pre(const LayerArgs& a, bool edge_path, const float* hV, float* wsA, float* wsN, float* wsP,
+                    cudaStream_t stream) {
+  if (opt_in_smem(node_pre_kernel)) return 1;
+  node_pre_kernel<<<a.row_tiles, kThreads, kSmemBytes, stream>>>(a.cx, path_weights(a.weights, a.layer, edge_path), hV,
+                                                                wsA, wsN, wsP);
+  return 0;
+}
+
+int launch_edge_node(const LayerArgs& a, const float* hE_in, int he_shared, const float* wsA, const float* wsN,
+                     const float* wsP, float* wsAcc, cudaStream_t stream) {
+  if (opt_in_smem(edge_node_kernel)) return 1;
+  edge_node_kernel<<<a.edge_tiles, kThreads, kSmemBytes, stream>>>(a.cx, path_weights(a.weights, a.layer, false), hE_in,
+                                                                  he_shared, wsA, wsN, wsP, wsAcc);
+  return 0;
+}
+
+int launch_node_post(const LayerArgs& a, const float* wsAcc, const float* msum, float* hV, cudaStream_t stream) {
+  if (opt_in_smem(node_post_kernel)) return 1;
+  PathWeights pn = path_weights(a.weights, a.layer, false);
+  const float* Lb = a.Lb;
+  NodePostWeights np{pn.W3, pn.B3, Lb + PP_OFF(L0_LN0_G), Lb + PP_OFF(L0_LN0_B), Lb + PP_OFF(L0_NF_WIN),
+                     Lb + PP_OFF(L0_NF_BIN), Lb + PP_OFF(L0_NF_WOUT), Lb + PP_OFF(L0_NF_BOUT), Lb + PP_OFF(L0_LN1_G),
+                     Lb + PP_OFF(L0_LN1_B)};
+  node_post_kernel<<<a.row_tiles, kThreads, kSmemBytes, stream>>>(a.cx, np, wsAcc, msum, hV, hV);
+  return 0;
+}
+
+int launch_edge_edge(const LayerArgs& a, const float* hE_in, int he_shared, const float* wsA, const float* wsN,
+                     const float* wsP, float* hE_out, cudaStream_t stream) {
+  if (opt_in_smem(edge_edge_kernel)) return 1;
+  const float* Lb = a.Lb;
+  EdgePostWeights ep{Lb + PP_OFF(L0_LN2_G), Lb + PP_OFF(L0_LN2_B), Lb + PP_OFF(L0_EF_WIN), Lb + PP_OFF(L0_EF_BIN),
+                     Lb + PP_OFF(L0_EF_WOUT), Lb + PP_OFF(L0_EF_BOUT), Lb + PP_OFF(L0_LN3_G), Lb + PP_OFF(L0_LN3_B)};
+  edge_edge_kernel<<<a.edge_tiles, kThreads, kSmemBytes, stream>>>(a.cx, path_weights(a.weights, a.layer, true), ep,
+                                                                  hE_in, he_shared, wsA, wsN, wsP, hE_out);
+  return 0;
+}
+
+}  // namespace
+
 // One IPMP layer on S*G residue rows (reference layers.py:119-148).
 //   hV [S*G][128] is updated in place; hE_in -> hE_out ([rows][K][128]; hE_in has G rows if he_shared else S*G).
 //   edge_update = 0 skips the edge half (the reference computes and discards it for the last layer, mpnn.py:53-62).
@@ -460,35 +526,60 @@ extern "C" int pp_ipmp_layer(const float* weights, int64_t layer, const float* g
                              int64_t K, int64_t S, float* hV, const float* hE_in, int64_t he_shared, float* hE_out,
                              int64_t edge_update, float* wsA, float* wsN, float* wsP, float* wsAcc,
                              cudaStream_t stream) {
-  PP_REQUIRE(weights && geo && nbr && mask_attend && msum && residue_mask && hV && hE_in, "null pointer");
-  PP_REQUIRE(wsA && wsN && wsP && wsAcc, "null workspace");
-  PP_REQUIRE(layer >= 0 && layer < 3, "layer out of range");
-  PP_REQUIRE(G > 0 && S > 0 && K > 0 && K <= PP_KMAX, "bad sizes");
+  LayerArgs a;
+  if (int rc = make_args(a, weights, layer, geo, nbr, mask_attend, residue_mask, G, K, S)) return rc;
+  PP_REQUIRE(msum && hV && hE_in && wsA && wsN && wsP && wsAcc, "null pointer");
   PP_REQUIRE(!edge_update || hE_out, "hE_out required when edge_update is set");
-  PP_REQUIRE(S * G < (1ll << 31) / 128, "too many rows");
-  if (opt_in_smem(node_pre_kernel) || opt_in_smem(edge_node_kernel) || opt_in_smem(node_post_kernel) ||
-      opt_in_smem(edge_edge_kernel))
-    return 1;
-  MpnnCtx cx{geo, nbr, mask_attend, residue_mask, (int)G, (int)K, (int)S};
-  const long long R = S * G;
-  const unsigned row_tiles = (unsigned)((R + kTileRows - 1) / kTileRows);
-  const unsigned edge_tiles = (unsigned)((R + 3) / 4);
-  const float* Lb = weights + layer * wl::kLayerStride;
-
-  PathWeights pn = path_weights(weights, (int)layer, false);
-  node_pre_kernel<<<row_tiles, kThreads, kSmemBytes, stream>>>(cx, pn, hV, wsA, wsN, wsP);
-  edge_node_kernel<<<edge_tiles, kThreads, kSmemBytes, stream>>>(cx, pn, hE_in, (int)he_shared, wsA, wsN, wsP, wsAcc);
-  NodePostWeights np{pn.W3, pn.B3, Lb + PP_OFF(L0_LN0_G), Lb + PP_OFF(L0_LN0_B), Lb + PP_OFF(L0_NF_WIN),
-                     Lb + PP_OFF(L0_NF_BIN), Lb + PP_OFF(L0_NF_WOUT), Lb + PP_OFF(L0_NF_BOUT), Lb + PP_OFF(L0_LN1_G),
-                     Lb + PP_OFF(L0_LN1_B)};
-  node_post_kernel<<<row_tiles, kThreads, kSmemBytes, stream>>>(cx, np, wsAcc, msum, hV, hV);
+  if (launch_node_pre(a, false, hV, wsA, wsN, wsP, stream)) return 1;
+  if (launch_edge_node(a, hE_in, (int)he_shared, wsA, wsN, wsP, wsAcc, stream)) return 1;
+  if (launch_node_post(a, wsAcc, msum, hV, stream)) return 1;
   if (edge_update) {
-    PathWeights pe = path_weights(weights, (int)layer, true);
-    node_pre_kernel<<<row_tiles, kThreads, kSmemBytes, stream>>>(cx, pe, hV, wsA, wsN, wsP);
-    EdgePostWeights ep{Lb + PP_OFF(L0_LN2_G), Lb + PP_OFF(L0_LN2_B), Lb + PP_OFF(L0_EF_WIN), Lb + PP_OFF(L0_EF_BIN),
-                       Lb + PP_OFF(L0_EF_WOUT), Lb + PP_OFF(L0_EF_BOUT), Lb + PP_OFF(L0_LN3_G), Lb + PP_OFF(L0_LN3_B)};
-    edge_edge_kernel<<<edge_tiles, kThreads, kSmemBytes, stream>>>(cx, pe, ep, hE_in, (int)he_shared, wsA, wsN, wsP,
-                                                                   hE_out);
+    if (launch_node_pre(a, true, hV, wsA, wsN, wsP, stream)) return 1;
+    if (launch_edge_edge(a, hE_in, (int)he_shared, wsA, wsN, wsP, hE_out, stream)) return 1;
   }
   return check_launch("pp_ipmp_layer");
+}
+
+// The four kernels of pp_ipmp_layer as separate entry points (same arguments), so that a caller can time or
+// re-order them.  path: 0 = node message path, 1 = edge message path.
+extern "C" int pp_ipmp_node_pre(const float* weights, int64_t layer, int64_t path, const float* geo, const int32_t* nbr,
+                                const float* mask_attend, const float* residue_mask, int64_t G, int64_t K, int64_t S,
+                                const float* hV, float* wsA, float* wsN, float* wsP, cudaStream_t stream) {
+  LayerArgs a;
+  if (int rc = make_args(a, weights, layer, geo, nbr, mask_attend, residue_mask, G, K, S)) return rc;
+  PP_REQUIRE(hV && wsA && wsN && wsP, "null pointer");
+  if (launch_node_pre(a, path != 0, hV, wsA, wsN, wsP, stream)) return 1;
+  return check_launch("pp_ipmp_node_pre");
+}
+
+extern "C" int pp_ipmp_edge_node(const float* weights, int64_t layer, const float* geo, const int32_t* nbr,
+                                 const float* mask_attend, const float* residue_mask, int64_t G, int64_t K, int64_t S,
+                                 const float* hE_in, int64_t he_shared, const float* wsA, const float* wsN,
+                                 const float* wsP, float* wsAcc, cudaStream_t stream) {
+  LayerArgs a;
+  if (int rc = make_args(a, weights, layer, geo, nbr, mask_attend, residue_mask, G, K, S)) return rc;
+  PP_REQUIRE(hE_in && wsA && wsN && wsP && wsAcc, "null pointer");
+  if (launch_edge_node(a, hE_in, (int)he_shared, wsA, wsN, wsP, wsAcc, stream)) return 1;
+  return check_launch("pp_ipmp_edge_node");
+}
+
+extern "C" int pp_ipmp_node_post(const float* weights, int64_t layer, const float* geo, const int32_t* nbr,
+                                 const float* mask_attend, const float* msum, const float* residue_mask, int64_t G,
+                                 int64_t K, int64_t S, const float* wsAcc, float* hV, cudaStream_t stream) {
+  LayerArgs a;
+  if (int rc = make_args(a, weights, layer, geo, nbr, mask_attend, residue_mask, G, K, S)) return rc;
+  PP_REQUIRE(msum && wsAcc && hV, "null pointer");
+  if (launch_node_post(a, wsAcc, msum, hV, stream)) return 1;
+  return check_launch("pp_ipmp_node_post");
+}
+
+extern "C" int pp_ipmp_edge_edge(const float* weights, int64_t layer, const float* geo, const int32_t* nbr,
+                                 const float* mask_attend, const float* residue_mask, int64_t G, int64_t K, int64_t S,
+                                 const float* hE_in, int64_t he_shared, const float* wsA, const float* wsN,
+                                 const float* wsP, float* hE_out, cudaStream_t stream) {
+  LayerArgs a;
+  if (int rc = make_args(a, weights, layer, geo, nbr, mask_attend, residue_mask, G, K, S)) return rc;
+  PP_REQUIRE(hE_in && wsA && wsN && wsP && hE_out, "null pointer");
+  if (launch_edge_edge(a, hE_in, (int)he_shared, wsA, wsN, wsP, hE_out, stream)) return 1;
+  return check_launch("pp_ipmp_edge_edge");
 }

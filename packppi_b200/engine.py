@@ -135,9 +135,22 @@ class Engine:
         hE0 = graph.hE0 if hE0 is None else hE0
         for layer in range(3):
             first = layer == 0
-            _lib.call("pp_ipmp_layer", W, layer, graph.geo, graph.nbr, graph.mask_attend, graph.msum, graph.mask, G, K,
-                      S, ws.hV, hE0 if first else ws.hE, 1 if first else 0, ws.hE, 1 if layer < 2 else 0, ws.wsA,
-                      ws.wsN, ws.wsP, ws.wsAcc)
+            hE_in, shared, edge = (hE0 if first else ws.hE), (1 if first else 0), layer < 2
+            common = (graph.geo, graph.nbr, graph.mask_attend)
+            if _lib.PROFILE is None:
+                _lib.call("pp_ipmp_layer", W, layer, *common, graph.msum, graph.mask, G, K, S, ws.hV, hE_in, shared,
+                          ws.hE, 1 if edge else 0, ws.wsA, ws.wsN, ws.wsP, ws.wsAcc, kernels=5 if edge else 3)
+                continue
+            # instrumented mode: the same five kernels through their own entry points
+            size = (graph.mask, G, K, S)
+            _lib.call("pp_ipmp_node_pre", W, layer, 0, *common, *size, ws.hV, ws.wsA, ws.wsN, ws.wsP, rows=S * G)
+            _lib.call("pp_ipmp_edge_node", W, layer, *common, *size, hE_in, shared, ws.wsA, ws.wsN, ws.wsP, ws.wsAcc,
+                      rows=S * G)
+            _lib.call("pp_ipmp_node_post", W, layer, *common, graph.msum, *size, ws.wsAcc, ws.hV, rows=S * G)
+            if edge:
+                _lib.call("pp_ipmp_node_pre", W, layer, 1, *common, *size, ws.hV, ws.wsA, ws.wsN, ws.wsP, rows=S * G)
+                _lib.call("pp_ipmp_edge_edge", W, layer, *common, *size, hE_in, shared, ws.wsA, ws.wsN, ws.wsP, ws.hE,
+                          rows=S * G)
         return ws.hV
 
     def network(self, graph, batch, chi, t):
