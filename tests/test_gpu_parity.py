@@ -16,6 +16,11 @@ pytestmark = pytest.mark.gpu
 CHI_TOL = 1e-4   # rad
 XYZ_TOL = 1e-3   # Angstrom
 ACT_TOL = 2e-4   # hidden activations (LayerNorm-scaled, O(1) values)
+# Embedded edge features: the two inter-residue dihedrals of every SELF edge (k = 0, j = i) are the angle between two
+# analytically parallel normals, i.e. arccos(1 +- rounding) = 0 or ~3.5e-4 * sqrt(n) rad depending on the last bit
+# (encoder.py:164-174,176-196).  The reference's value there is rounding noise, ours is different rounding noise; after
+# the 468->128 Linear and LayerNorm it shows up as a few 1e-4 in h_E0.  Everything downstream is gated at ACT_TOL.
+HE0_TOL = 1e-3
 
 
 @pytest.fixture(scope="module")
@@ -71,7 +76,8 @@ def test_network_probe(case, model, dev):
     eng, graph = model._graph(bd)
     att = graph.mask_attend.reshape(B, L, -1)[:, rows].cpu()[..., None]
     hE0 = graph.hE0.reshape(B, L, graph.K, 128)[:, rows].cpu()
-    assert ((hE0 - tt(g["ref_probe_hE0_rows"])) * att).abs().max() < ACT_TOL
+    assert ((hE0 - tt(g["ref_probe_hE0_rows"])) * att).abs().max() < HE0_TOL
+    assert ((hE0 - tt(g["ref_probe_hE0_rows"])) * att)[:, :, 1:].abs().max() < ACT_TOL  # all but the self edge
     # encoder through its own forward (reference signature)
     x = tt(g["in_probe_SC_D"]).to(dev)
     sc = torch.stack((torch.sin(x), torch.cos(x)), -1) * bd.SC_D_mask[..., None]
