@@ -1,0 +1,199 @@
+"""CPU tests of the host side: C-ABI library exports, weight packing, tables, featuriser / PDB I/O, sharding."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+HAVE_REF = os.path.isdir("/root/reference/src")
+
+
+def test_library_loads_and_exports_every_header_symbol():
+    from packppi_b200 import _lib
+    lib = _lib.load()
+    with open(os.path.join(ROOT, "include", "packppi_b200.h")) as f:
+        names = set(re.findall(r"\b(pp_\w+)\s*\(", f.read()))
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.pp_abi_version() == 1
+    assert set(_lib.SIGNATURES) <= names and set(_lib.KERNELS) == set(_lib.SIGNATURES)
+
+
+def test_no_cpu_fallback():
+    import packppi_b200 as pp
+    from packppi_b200 import synthetic
+    b = synthetic.make_complex((6, 5), seed=1)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pp.get_atom14_coords(b.X, b.residue_type, b.BB_D, b.SC_D)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pp.compute_residue_clash(b, b.SC_D)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pp.proximal_optimizer(b, b.SC_D, 12.0, 0.5, 1.0, 2)
+    m = pp.TDiffusionModule()
+    with pytest.raises(RuntimeError):
+        m.sampling(b)
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from packppi_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libpackppi_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_weight_layout_and_packing():
+    from packppi_b200 import _lib, weights
+    layout, total = _lib.layout()
+    sd = weights.make_state_dict(3)
+    assert weights.num_parameters() == 1439172
+    blob = weights.pack_weights(sd, layout, total)
+    assert blob.numel() == total and all(off % 32 == 0 for off, _ in layout.values())
+
+    def view(name, rows, cols):
+        off, _ = layout[name]
+        return blob[off:off + rows * cols].reshape(rows, cols)
+
+    Win = sd["mpnn.mpnn_layers.1.edge_message_fn.W_in.weight"]
+    assert torch.equal(view("L1_E_WAG", 160, 128), torch.cat([Win[:, :128].t(), Win[:, 384:416].t()]))
+    assert torch.equal(view("L1_E_WEG", 168, 128), torch.cat([Win[:, 128:256].t(), Win[:, 416:456].t()]))
+    assert torch.equal(view("L1_E_WN", 128, 128), Win[:, 256:384].t())
+    We = sd["encoder.edge_embedding.weight"]
+    Wt = view("ENC_EDGE_WT", 496, 128)
+    assert torch.equal(Wt[:400], We[:, 65:465].t()) and torch.equal(Wt[400:465], We[:, :65].t())
+    assert torch.equal(Wt[480:483], We[:, 465:].t()) and Wt[465:480].abs().sum() == 0 and Wt[483:].abs().sum() == 0
+    assert torch.equal(view("L2_NF_WOUT", 512, 128), sd["mpnn.mpnn_layers.2.node_dense.W_out.weight"].t())
+    assert torch.equal(view("DEC_W3", 16, 4), sd["decoder_score.2.W_out.weight"].t())
+    bad = dict(sd)
+    bad["encoder.node_embedding.weight"] = torch.zeros(128, 50)
+    with pytest.raises(RuntimeError, match="shape"):
+        weights.pack_weights(bad, layout, total)
+
+
+def test_module_state_dict_keys_match_reference_layout():
+    from packppi_b200 import TDiffusionModule, weights
+    m = TDiffusionModule()
+    assert list(m.state_dict().keys()) == list(weights.shapes().keys())
+    assert sum(p.numel() for p in m.parameters()) == weights.num_parameters()
+
+
+def test_ode_coefficients_closed_form():
+    """c = 0.5 g^2 dt, w = 3 / (alpha + 3 (1 - alpha)) with sigma = exp(ln(0.01 pi) + ln(100) t) (SURVEY.md §8a')."""
+    from packppi_b200.engine import Engine
+    co = Engine.ode_coefficients(30, 3)
+    assert len(co) == 30 and abs(co[0][0] - 1.0) < 1e-7
+    for t, c, w in co:
+        sigma = np.exp(np.log(0.01 * np.pi) + np.log(100.0) * t)
+        g2 = sigma ** 2 * 2 * np.log(100.0)
+        alpha = 1 - (sigma / np.pi) ** 2
+        assert abs(c - 0.5 * g2 / 30) < 1e-5 * max(1.0, c)
+        assert abs(w - 3 / (alpha + 3 * (1 - alpha))) < 1e-5
+
+
+def test_dist_bounds_and_reach():
+    from packppi_b200 import tables
+    lo, hi = tables.dist_bounds(0.5, 12.0)
+    assert lo.shape == (21, 14, 14) and lo.dtype == np.float32
+    assert np.array_equal(lo, lo.transpose(0, 2, 1)) and np.array_equal(hi, hi.transpose(0, 2, 1))
+    assert (tables.max_reach()[:20] > 2.3).all() and tables.max_reach().max() < 12.0
+    assert tables.packed_geometry().shape == (21, tables.GEO_STRIDE)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree not mounted")
+def test_tables_equal_reference():
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_tables
+    from packppi_b200 import tables
+    t, rc = gen_tables.build_tables()
+    for k, v in tables.raw().items():
+        assert np.array_equal(v, t[k]), k
+    for cot, vtf in ((0.5, 12.0), (1.5, 15.0)):
+        ref = rc.make_atom14_dists_bounds(overlap_tolerance=cot, bond_length_tolerance_factor=vtf)
+        lo, hi = tables.dist_bounds(cot, vtf)
+        assert np.array_equal(lo, ref["lower_bound"]) and np.array_equal(hi, ref["upper_bound"])
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree not mounted")
+@pytest.mark.parametrize("name,case", [("1BRS", "1brs"), ("T1124_lig", "t1124")])
+def test_pdb_reader_and_featuriser_reproduce_golden_inputs(name, case):
+    """packppi_b200.pdb + featurize against the batch the reference's prot_to_data produced for the golden files."""
+    from packppi_b200 import featurize, pdb
+    from util import load_golden
+    _, gb = load_golden(case)
+    b = featurize.protein_to_batch(pdb.read_pdb(f"/root/reference/data/{name}.pdb"))
+    for k, v in gb.items():
+        if torch.is_tensor(v):
+            assert v.dtype == b[k].dtype and torch.equal(v, b[k]), k
+
+
+def test_pdb_write_read_round_trip(tmp_path):
+    from packppi_b200 import pdb
+    from util import load_golden
+    _, b = load_golden("syn64")
+    from packppi_b200 import tables
+    prot = dict(atom_positions=np.round(b.X[0].numpy().astype(np.float64), 3), atom_mask=b.atom_mask[0].numpy(),
+                aaindex=b.residue_type[0].numpy(), residue_index=np.arange(1, 65),
+                chain_id=np.array(["A"] * 32 + ["B"] * 32))
+    prot["atom_positions"][prot["atom_mask"] == 0] = np.nan
+    path = tmp_path / "x.pdb"
+    pdb.write_pdb(prot, str(path))
+    back = pdb.read_pdb(str(path))
+    assert np.array_equal(back["aaindex"], prot["aaindex"]) and np.array_equal(back["atom_mask"], prot["atom_mask"])
+    assert np.allclose(np.nan_to_num(back["atom_positions"]), np.nan_to_num(prot["atom_positions"]), atol=1e-3)
+    assert list(back["chain_id"]) == list(prot["chain_id"]) and tables.restypes()[0] == "A"
+
+
+def test_collate_pads_like_reference():
+    from packppi_b200 import collate, synthetic
+    items = [synthetic.make_complex((4, 3), seed=1), synthetic.make_complex((6, 5), seed=2)]
+    b = collate(items)
+    assert b.X.shape == (2, 11, 14, 3) and b.num_proteins == 2 and b.max_size == 11
+    assert torch.equal(b.X[0, :7], items[0].X[0]) and b.X[0, 7:].abs().sum() == 0
+    assert b.residue_mask[0].tolist() == [1.0] * 7 + [0.0] * 4 and b.chi_1pi_periodic_mask.dtype == torch.bool
+
+
+def test_partition_is_balanced_and_complete():
+    from packppi_b200 import shard
+    lengths = [800, 200, 640, 333, 512, 250, 799, 410]
+    for world in (1, 2, 4, 8):
+        plan = shard.partition(lengths, world)
+        assert sorted(i for p in plan for i in p) == list(range(len(lengths)))
+        loads = [sum(lengths[i] for i in p) for p in plan]
+        assert max(loads) - min(loads) <= max(lengths)
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from packppi_b200 import shard, synthetic
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    batches = [synthetic.make_complex((n, 3), seed=n) for n in (9, 4, 7, 5, 6)]
+    calls = []
+
+    def fake_sampler(b, S):  # deterministic stand-in for model.sampling(b, n_samples=S)
+        calls.append(int(b.max_size))
+        return torch.stack([b.SC_D * (s + 1) for s in range(S)])
+
+    out = shard.sample_sharded(fake_sampler, batches, 3)
+    ok = all(torch.equal(o, torch.stack([b.SC_D[0] * (s + 1) for s in range(3)])) for o, b in zip(out, batches))
+    q.put((rank, ok, sorted(calls)))
+    dist.destroy_process_group()
+
+
+def test_sharded_sampling_over_two_gloo_ranks():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res)
+    done = sorted(sum((c for _, _, c in res), []))
+    assert done == [7, 8, 9, 10, 12]  # every complex sampled exactly once across the two ranks
