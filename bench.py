@@ -160,7 +160,9 @@ def run_reference(args):
 
 
 def workload_config(args):
-    return {"workload": f"sweep of {args.complexes} synthetic 2-chain complexes, L~U{{200..800}} (seed 64) x "
+    return {"kernel_mode": os.environ.get("PACKPPI_B200_MODE", "tf32x3"),
+            "kernel_cluster": int(os.environ.get("PACKPPI_B200_CLUSTER", "1")),
+            "workload": f"sweep of {args.complexes} synthetic 2-chain complexes, L~U{{200..800}} (seed 64) x "
                         f"{N_SAMPLES} diffusion samples x {N_ODE} reverse-ODE steps, micro-batches of {MICRO} complexes; "
                         "BASELINE.json configs[4]",
             "weights": "random init, packppi_b200.weights.make_state_dict(0)", "samples_per_complex": N_SAMPLES,
@@ -255,10 +257,12 @@ def main():
     h2d = sum(b.nbytes() for b in micro_host)
     d2h = sum(int(b.X.shape[0] * b.X.shape[1]) for b in micro_host) * N_SAMPLES * 4 * 4
 
-    # instrumented pass: CUDA events around every launch of the dominant kernel
-    _lib.PROFILE = {"pp_ipmp_edge_edge": []}
+    # instrumented pass: CUDA events around every launch of the dominant kernel (the per-edge edge update)
+    mode, cluster = model.kernel_mode, model.kernel_cluster
+    pkey = "pp_ipmp_edge_edge" if mode == "fp32" else "pp_ipmp_edge_tc:edge"
+    _lib.PROFILE = {pkey: []}
     t_pass = timed(micro_dev, False, 1)
-    ev = _lib.PROFILE["pp_ipmp_edge_edge"]
+    ev = _lib.PROFILE[pkey]
     _lib.PROFILE = None
     torch.cuda.synchronize()
     k_ms = [a.elapsed_time(b) for a, b, _ in ev]
@@ -268,7 +272,10 @@ def main():
         tot_ms, tot_rows = sum(k_ms), sum(k_rows)
         tflops = EDGE_KERNEL_FLOP_PER_RES * tot_rows / (tot_ms * 1e-3) / 1e12
         gbs = EDGE_KERNEL_BYTES_PER_RES * tot_rows / (tot_ms * 1e-3) / 1e9
-        roof = {"kernel": "edge_edge_kernel (per-edge message MLP + FFN, fp32 FFMA)", "bound": "tensor",
+        kname = {"fp32": "edge_edge_kernel (per-edge message MLP + FFN, fp32 FFMA on CUDA cores)",
+                 "tf32x3": "edge_tc_kernel<edge> (per-edge message MLP + FFN, tcgen05 split-TF32, 3 MMAs per product)",
+                 "tf32": "edge_tc_kernel<edge> (per-edge message MLP + FFN, tcgen05 plain TF32)"}[mode]
+        roof = {"kernel": kname, "bound": "tensor",
                 "achieved": tflops, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": tflops / peaks["tf_sust"],
                 "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
                 "traffic": None, "avg_launch_ms": tot_ms / len(k_ms), "launches": len(k_ms),

@@ -87,6 +87,16 @@ int pp_ipmp_edge_edge(const float* weights, int64_t layer, const float* geo, con
                       const float* hE_in, int64_t he_shared, const float* wsA, const float* wsN, const float* wsP,
                       float* hE_out, pp_stream_t stream);
 
+/* Tensor-core (tcgen05 / TMEM) version of pp_ipmp_edge_node (path 0) and pp_ipmp_edge_edge (path 1): same inputs,
+ * same outputs.  wstream = operand images of this layer and path (pp_tc_stream_floats() floats, built by
+ * packppi_b200.weights.pack_tc_stream).  passes 3 = split TF32 (fp32-grade), 1 = plain TF32; cluster = 1, 2 or 4
+ * CTAs that share (multicast) the weight stream.  out = accsum [S*G][128] or hE_out [S*G][K][128]. */
+int64_t pp_tc_stream_floats(void);
+int pp_ipmp_edge_tc(const float* weights, int64_t layer, int64_t path, const float* wstream, const float* geo,
+                    const int32_t* nbr, const float* mask_attend, int64_t G, int64_t K, int64_t S,
+                    const float* hE_in, int64_t he_shared, const float* wsA, const float* wsN, const float* wsP,
+                    float* out, int64_t passes, int64_t cluster, pp_stream_t stream);
+
 /* decoder_score (models/TorsionalDiffusion.py:62-68,106-108) and, if do_step, both SO2VESchedule.step calls in ode
  * mode plus wrap and mask (models/components/schedule.py:198-235, TorsionalDiffusion.py:272-280):
  *   chi <- wrap(chi + [step_mask] c_ode (score * w_anneal)) * chi_mask.

@@ -25,6 +25,7 @@ SIGNATURES = {
     "pp_ipmp_edge_node": "p" "i" "pppp" "iii" "p" "i" "pppp" "s",
     "pp_ipmp_node_post": "p" "i" "ppppp" "iii" "pp" "s",
     "pp_ipmp_edge_edge": "p" "i" "pppp" "iii" "p" "i" "pppp" "s",
+    "pp_ipmp_edge_tc": "p" "ii" "pppp" "iii" "p" "i" "pppp" "ii" "s",
     "pp_decode_step": "pp" "ii" "p" "i" "ff" "ppp" "s",
     "pp_atom14_fwd": "pppp" "ii" "p" "s",
     "pp_clash_neighbours": "ppppp" "ii" "f" "i" "pppp" "s",
@@ -39,7 +40,7 @@ _lib = None
 
 # kernels launched per entry point (pp_ipmp_layer: 3, or 5 with the edge update - the caller passes `kernels=`)
 KERNELS = {"pp_knn_build": 1, "pp_geometry_build": 1, "pp_edge_embed": 1, "pp_node_embed": 1, "pp_ipmp_layer": 5,
-           "pp_ipmp_node_pre": 1, "pp_ipmp_edge_node": 1, "pp_ipmp_node_post": 1, "pp_ipmp_edge_edge": 1,
+           "pp_ipmp_node_pre": 1, "pp_ipmp_edge_node": 1, "pp_ipmp_node_post": 1, "pp_ipmp_edge_edge": 1, "pp_ipmp_edge_tc": 1,
            "pp_decode_step": 1, "pp_atom14_fwd": 1, "pp_clash_neighbours": 1, "pp_clash_fwd_bwd": 2,
            "pp_prox_init": 4, "pp_prox_step": 3, "pp_selftest_umma": 1}
 LAUNCHES = 0      # running count of kernels launched through call()
@@ -56,7 +57,7 @@ def load():
     lib = ctypes.CDLL(LIB_PATH)
     lib.pp_last_error.restype = ctypes.c_char_p
     lib.pp_abi_version.restype = ctypes.c_int
-    for fn in ("pp_layout_count", "pp_layout_total_floats", "pp_geo_stride", "pp_table_stride"):
+    for fn in ("pp_layout_count", "pp_layout_total_floats", "pp_geo_stride", "pp_table_stride", "pp_tc_stream_floats"):
         getattr(lib, fn).restype = _I
     lib.pp_prox_partial_floats.restype = _I
     lib.pp_prox_partial_floats.argtypes = [_I]
@@ -106,7 +107,7 @@ def ptr(t):
     return t.data_ptr()
 
 
-def call(name, *args, device=None, kernels=None, rows=0):
+def call(name, *args, device=None, kernels=None, rows=0, tag=None):
     """Invoke an entry point on torch's current stream; tensors are passed as device pointers."""
     global LAUNCHES
     lib = load()
@@ -124,7 +125,7 @@ def call(name, *args, device=None, kernels=None, rows=0):
     _check_device(lib, dev.index if dev.index is not None else torch.cuda.current_device())
     with torch.cuda.device(dev):
         cur = torch.cuda.current_stream()
-        prof = PROFILE.get(name) if PROFILE is not None else None
+        prof = PROFILE.get(name if tag is None else f"{name}:{tag}") if PROFILE is not None else None
         if prof is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(cur)

@@ -1,0 +1,529 @@
+// Per-edge message MLPs of the IPMP layers on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Same mathematics as edge_node_kernel / edge_edge_kernel in mpnn.cu (reference layers.py:119-148), same operand
+// split (only the 168-wide [h_E | pair geometry] part of the first Linear is per edge).  One CTA = one tile of 128
+// edges (4 residues x 32 neighbours) = the M dimension of a 128 x 128 UMMA; the whole GEMM chain of the tile stays on
+// chip:
+//   warps 0-3  row workers: thread = edge row = TMEM lane.  Build the first A operand, then act as the epilogue of
+//              every GEMM: tcgen05.ld 32 columns -> bias / ReLU / LayerNorm (a row is thread-private, no shuffles) ->
+//              next A operand, written 32 columns at a time into a shared-memory ring (or into TMEM for the FFN input)
+//   warp 4     MMA issuer (one elected lane): tcgen05.mma kind::tf32, accumulators ping-pong between two 128-column
+//              TMEM regions, completion signalled with tcgen05.commit on mbarriers
+//   warp 5     weight loader: cp.async.bulk of pre-packed operand images (K-major core-matrix layout, consumption
+//              order, see pack_tc_stream in packppi_b200/weights.py) into a ring; with CLUSTER > 1 every CTA fetches
+//              1/CLUSTER of each image and multicasts it to the whole cluster, dividing the L2 -> SM weight traffic
+// A chunks are consumed by the MMA warp as soon as they are written, so the epilogue of GEMM n overlaps the MMAs of
+// GEMM n+1.  The FFN input e = LayerNorm(...) is kept in TMEM as (hi, lo) and fed to the four 128-wide slices of
+// the 128 -> 512 Linear as a TMEM A operand; hi + lo is e exactly, so it also serves as the residual.
+//
+// Precision (PASSES): 3 = split TF32, x = hi + lo with hi = x truncated to TF32: hi*hi + hi*lo + lo*hi keeps 21+
+// mantissa bits per product with fp32 accumulation (parity mode); 1 = plain TF32 (fast mode, looser tolerance).
+#include "common.cuh"
+#include "umma.cuh"
+#include "weights_layout.h"
+
+namespace pp {
+namespace tc {
+
+using namespace umma;
+
+constexpr int kRows = 128;
+constexpr int kKC = 32;
+constexpr int kSA = 3, kSB = 3;
+constexpr int kImgFloats = kRows * kKC;          // one operand image (hi or lo) of a 32-column chunk
+constexpr uint32_t kImgBytes = kImgFloats * 4;   // 16 KB
+constexpr int kSlotFloats = 2 * kImgFloats;      // hi + lo
+constexpr int kThreadsTC = 192;
+constexpr uint32_t kLbo = kRows * 16, kSbo = 128;
+constexpr uint32_t kIdesc = idesc_tf32(128, 128);
+
+constexpr int kChunksNode = 10;                  // G1 (5x32 + 8), G2 (4x32)
+constexpr int kChunksEdge = 6 + 4 + 4 + 4 * 8;   // + G3, 4 x (FFN-in slice, FFN-out slice)
+constexpr long long kStreamFloats = 2LL * 128 * (168 + 128 + 128 + 4 * 256);
+
+constexpr size_t kBarBytes = (2 * kSA + 2 * kSB + 2 + 1) * 8;
+constexpr size_t kSmemTC = (size_t)(kSA + kSB) * kSlotFloats * 4 + kBarBytes + 16;
+
+struct Args {
+  const float* geo; const int* nbr; const float* matt;
+  int G, K, S;
+  const float* wstream;   // operand images of this layer / path
+  const float *B2, *B3, *LNG, *LNB, *BIN, *BOUT, *LN3G, *LN3B;
+  const float* hE_in; int he_shared;
+  const float *A, *Nn, *pglob;
+  float* out;             // node path: accsum [R][128]; edge path: hE_out [R][K][128]
+};
+
+struct Ring {
+  int idx; uint32_t phase;
+  __device__ __forceinline__ void next(int n) { if (++idx == n) { idx = 0; phase ^= 1; } }
+};
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mc(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+
+// write this thread's row of a chunk (kc columns, v[0..kc)) into an A ring slot in the UMMA core-matrix layout
+template <int PASSES>
+__device__ __forceinline__ void put_chunk(float* slot, int m, const float* v, int kc) {
+  float* hi = slot;
+  float* lo = slot + kImgFloats;
+  const int base = (m >> 3) * 32 + (m & 7) * 4;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    if (u * 4 < kc) {
+      float4 h, l;
+      split_tf32(v[u * 4 + 0], h.x, l.x); split_tf32(v[u * 4 + 1], h.y, l.y);
+      split_tf32(v[u * 4 + 2], h.z, l.z); split_tf32(v[u * 4 + 3], h.w, l.w);
+      *reinterpret_cast<float4*>(hi + u * (kRows * 4) + base) = h;
+      if (PASSES == 3) *reinterpret_cast<float4*>(lo + u * (kRows * 4) + base) = l;
+    }
+  }
+}
+
+// 32 consecutive per-column parameters (bias, LayerNorm gain ...): the address is warp-uniform, 8 broadcast loads
+__device__ __forceinline__ void ld32(const float* __restrict__ p, float (&d)[32]) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    float4 x = *reinterpret_cast<const float4*>(p + u * 4);
+    d[u * 4] = x.x; d[u * 4 + 1] = x.y; d[u * 4 + 2] = x.z; d[u * 4 + 3] = x.w;
+  }
+}
+
+template <bool EDGE, int PASSES, int CLUSTER>
+__global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* Aring = reinterpret_cast<float*>(smem);
+  float* Bring = Aring + kSA * kSlotFloats;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Bring + kSB * kSlotFloats);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + kSA;
+  uint64_t* b_full = a_empty + kSA;
+  uint64_t* b_empty = b_full + kSB;
+  uint64_t* acc_full = b_empty + kSB;  // [2]
+  uint64_t* wk_done = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wk_done + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int R = a.S * a.G, K = a.K;
+  const int rb = blockIdx.x * 4;
+  constexpr int NCHUNK = EDGE ? kChunksEdge : kChunksNode;
+  constexpr uint16_t kMask = (uint16_t)((1u << CLUSTER) - 1);
+
+  if (tid == 0) {
+    for (int i = 0; i < kSA; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < kSB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], CLUSTER); }
+    mbar_init(&acc_full[0], 1);
+    mbar_init(&acc_full[1], 1);
+    mbar_init(wk_done, 128);
+    mbar_fence_init();
+  }
+  if (warp == 4) tmem_alloc<512>(tmem_slot);
+  fence_before_sync();
+  __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();  // every CTA's barriers exist before any remote arrive / multicast
+  fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t ACC0 = tmem, ACC1 = tmem + 128, EH = tmem + 256, EL = tmem + 384;
+
+  if (warp == 5) {
+    // ------------------------------------------------------------------ weight loader
+    if (lane == 0) {
+      Ring rb_{0, 1};
+      const float* src = a.wstream;
+      const uint32_t crank = (CLUSTER > 1) ? cluster_rank() : 0;
+      for (int i = 0; i < NCHUNK; ++i) {
+        const int kc = (i == 5) ? 8 : kKC;
+        const uint32_t img = (uint32_t)kRows * kc * 4;
+        mbar_wait(&b_empty[rb_.idx], rb_.phase);
+        mbar_arrive_expect_tx(&b_full[rb_.idx], img * (PASSES == 3 ? 2 : 1));
+        float* dst = Bring + rb_.idx * kSlotFloats;
+        if (CLUSTER == 1) {
+          bulk_g2s(dst, src, img, &b_full[rb_.idx]);
+          if (PASSES == 3) bulk_g2s(dst + kImgFloats, src + kRows * kc, img, &b_full[rb_.idx]);
+        } else {
+          const uint32_t piece = img / CLUSTER, po = crank * piece / 4;
+          bulk_g2s_mc(dst + po, src + po, piece, &b_full[rb_.idx], kMask);
+          if (PASSES == 3) bulk_g2s_mc(dst + kImgFloats + po, src + kRows * kc + po, piece, &b_full[rb_.idx], kMask);
+        }
+        src += 2 * kRows * kc;
+        rb_.next(kSB);
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      Ring ra{0, 0}, rbq{0, 0};
+      uint32_t wk_phase = 0;
+      auto chunk = [&](bool ss, uint32_t acc, uint32_t a_col, int kc, bool fresh) {
+        if (ss) mbar_wait(&a_full[ra.idx], ra.phase);
+        mbar_wait(&b_full[rbq.idx], rbq.phase);
+        fence_after_sync();
+        const uint32_t as = smem_u32(Aring + ra.idx * kSlotFloats), bs = smem_u32(Bring + rbq.idx * kSlotFloats);
+#pragma unroll
+        for (int p = 0; p < PASSES; ++p) {
+          const uint32_t ao = (p == 2) ? kImgBytes : 0, bo = (p == 1) ? kImgBytes : 0;
+          for (int kk = 0; kk < kc; kk += 8) {
+            const uint64_t bd = smem_desc(bs + bo + (kk / 4) * kLbo, kLbo, kSbo);
+            const uint32_t accum = (fresh && p == 0 && kk == 0) ? 0u : 1u;
+            if (ss) mma_tf32_ss(acc, smem_desc(as + ao + (kk / 4) * kLbo, kLbo, kSbo), bd, kIdesc, accum);
+            else mma_tf32_ts(acc, ((p == 2) ? EL : EH) + a_col + kk, bd, kIdesc, accum);
+          }
+        }
+        if (CLUSTER == 1) mma_commit(&b_empty[rbq.idx]); else mma_commit_mc(&b_empty[rbq.idx], kMask);
+        rbq.next(kSB);
+        if (ss) { mma_commit(&a_empty[ra.idx]); ra.next(kSA); }
+      };
+      // G1: [h_E | pair] (168) -> ACC0
+      for (int c = 0; c < 6; ++c) chunk(true, ACC0, 0, c == 5 ? 8 : kKC, c == 0);
+      mma_commit(&acc_full[0]);
+      // G2 -> ACC1
+      for (int c = 0; c < 4; ++c) chunk(true, ACC1, 0, kKC, c == 0);
+      mma_commit(&acc_full[1]);
+      if (EDGE) {
+        // G3 -> ACC0
+        for (int c = 0; c < 4; ++c) chunk(true, ACC0, 0, kKC, c == 0);
+        mma_commit(&acc_full[0]);
+        for (int j = 0; j < 4; ++j) {
+          mbar_wait(wk_done, wk_phase);  // e is in TMEM (j = 0) / ACC1 has been drained (j > 0)
+          wk_phase ^= 1;
+          fence_after_sync();
+          for (int c = 0; c < 4; ++c) chunk(false, ACC1, c * kKC, kKC, c == 0);  // FFN-in slice j: A = e from TMEM
+          mma_commit(&acc_full[1]);
+          for (int c = 0; c < 4; ++c) chunk(true, ACC0, 0, kKC, j == 0 && c == 0);  // FFN-out slice j accumulates
+        }
+        mma_commit(&acc_full[0]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ row workers (thread = edge row = TMEM lane)
+    const int m = tid, rl = warp, k = lane;
+    const int r = rb + rl;
+    const bool in_range = r < R && k < K;
+    const int rr = min(r, R - 1);
+    const int s = rr / a.G, g = rr - s * a.G;
+    const float matt = in_range ? a.matt[(size_t)g * K + k] : 0.f;
+    const int jrow = in_range ? s * a.G + a.nbr[(size_t)g * K + k] : rr;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const float* hrow = a.hE_in + ((size_t)(a.he_shared ? g : rr) * K + (in_range ? k : 0)) * 128;
+    Ring pa{0, 1};
+    uint32_t accph[2] = {0, 0};
+    float v[32];
+
+    auto publish = [&](const float* vals, int kc) {
+      mbar_wait(&a_empty[pa.idx], pa.phase);
+      put_chunk<PASSES>(Aring + pa.idx * kSlotFloats, m, vals, kc);
+      fence_async_smem();
+      mbar_arrive(&a_full[pa.idx]);
+      pa.next(kSA);
+    };
+    auto load_acc = [&](uint32_t acc, int c) {
+      uint32_t u[32];
+      tmem_ld32(acc + lane_base + c * 32, u);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(u[i]);
+    };
+    auto store_tmem = [&](uint32_t col, const float* vals) {
+      uint32_t u[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) u[i] = __float_as_uint(vals[i]);
+      tmem_st32(col + lane_base, u);
+    };
+
+    // ---- first A operand: h_E row (4 chunks) and the pair geometry (32 + 8 columns)   (layers.py:93-115)
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        float4 x = in_range ? *reinterpret_cast<const float4*>(hrow + c * 32 + u * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[u * 4] = x.x; v[u * 4 + 1] = x.y; v[u * 4 + 2] = x.z; v[u * 4 + 3] = x.w;
+      }
+      publish(v, kKC);
+    }
+    {
+      const float* fr = a.geo + (size_t)g * PP_GEO_STRIDE;
+      const float* pi = a.pglob + (size_t)rr * 24;
+      const float* pj = a.pglob + (size_t)jrow * 24;
+      float ng[8];
+#pragma unroll
+      for (int pt = 0; pt < 8; ++pt) {
+        float jx = pj[pt * 3], jy = pj[pt * 3 + 1], jz = pj[pt * 3 + 2];
+        float dx = jx - fr[9], dy = jy - fr[10], dz = jz - fr[11];
+        float qx = fr[0] * dx + fr[3] * dy + fr[6] * dz;
+        float qy = fr[1] * dx + fr[4] * dy + fr[7] * dz;
+        float qz = fr[2] * dx + fr[5] * dy + fr[8] * dz;
+        float gx = pi[pt * 3] - jx, gy = pi[pt * 3 + 1] - jy, gz = pi[pt * 3 + 2] - jz;
+        v[pt * 3] = qx; v[pt * 3 + 1] = qy; v[pt * 3 + 2] = qz;
+        v[24 + pt] = sqrtf(qx * qx + qy * qy + qz * qz + 1e-8f);
+        ng[pt] = sqrtf(gx * gx + gy * gy + gz * gz + 1e-8f);
+      }
+      publish(v, kKC);
+      publish(ng, 8);
+    }
+
+    // ---- epilogue of G1: x1 = relu(acc + A_i + N_j)
+    mbar_wait(&acc_full[0], accph[0]); accph[0] ^= 1;
+    fence_after_sync();
+    {
+      const float* Ai = a.A + (size_t)rr * 128;
+      const float* Nj = a.Nn + (size_t)jrow * 128;
+      for (int c = 0; c < 4; ++c) {
+        load_acc(ACC0, c);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float4 x = *reinterpret_cast<const float4*>(Ai + c * 32 + u * 4);
+          float4 y = *reinterpret_cast<const float4*>(Nj + c * 32 + u * 4);
+          v[u * 4 + 0] = fmaxf(v[u * 4 + 0] + x.x + y.x, 0.f);
+          v[u * 4 + 1] = fmaxf(v[u * 4 + 1] + x.y + y.y, 0.f);
+          v[u * 4 + 2] = fmaxf(v[u * 4 + 2] + x.z + y.z, 0.f);
+          v[u * 4 + 3] = fmaxf(v[u * 4 + 3] + x.w + y.w, 0.f);
+        }
+        publish(v, kKC);
+      }
+    }
+    // ---- epilogue of G2: x2 = relu(acc + b2)
+    mbar_wait(&acc_full[1], accph[1]); accph[1] ^= 1;
+    fence_after_sync();
+    if (!EDGE) {
+      // node path: masked sum over the 32 edges of the residue (= the 32 lanes of this warp), layers.py:125-127
+      for (int c = 0; c < 4; ++c) {
+        load_acc(ACC1, c);
+        float b[32];
+        ld32(a.B2 + c * 32, b);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = (matt != 0.f) ? fmaxf(v[i] + b[i], 0.f) : 0.f;
+        // transpose-reduce: after the 5 steps lane l holds the column sum of column l
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+          const bool upper = (lane & step) != 0;
+#pragma unroll
+          for (int i = 0; i < step; ++i) {
+            float keep = upper ? v[i + step] : v[i];
+            float send = upper ? v[i] : v[i + step];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+          }
+        }
+        if (r < R) a.out[(size_t)r * 128 + c * 32 + lane] = v[0];
+      }
+    } else {
+      for (int c = 0; c < 4; ++c) {
+        load_acc(ACC1, c);
+        float b[32];
+        ld32(a.B2 + c * 32, b);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + b[i], 0.f);
+        publish(v, kKC);
+      }
+      // ---- epilogue of G3: e = LN2(h_E + mask * (acc + b3))   (layers.py:139-142); e -> TMEM as (hi, lo)
+      mbar_wait(&acc_full[0], accph[0]); accph[0] ^= 1;
+      fence_after_sync();
+      float sum = 0.f;
+      for (int c = 0; c < 4; ++c) {
+        load_acc(ACC0, c);
+        float b[32];
+        ld32(a.B3 + c * 32, b);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float4 h = in_range ? *reinterpret_cast<const float4*>(hrow + c * 32 + u * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float hh[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            int i = u * 4 + q;
+            v[i] = hh[q] + ((matt != 0.f) ? v[i] + b[i] : 0.f);
+            sum += v[i];
+          }
+        }
+        store_tmem(ACC0 + c * 32, v);
+      }
+      tmem_st_wait();
+      const float mean = sum * (1.f / 128.f);
+      float var = 0.f;
+      for (int c = 0; c < 4; ++c) {
+        load_acc(ACC0, c);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { float d = v[i] - mean; var += d * d; }
+      }
+      const float rstd = rsqrtf(var * (1.f / 128.f) + 1e-5f);
+      for (int c = 0; c < 4; ++c) {
+        load_acc(ACC0, c);
+        float lo[32], gm[32];
+        ld32(a.LNG + c * 32, gm);
+        ld32(a.LNB + c * 32, lo);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float e = (v[i] - mean) * rstd * gm[i] + lo[i];
+          split_tf32(e, v[i], lo[i]);
+        }
+        store_tmem(EH + c * 32, v);
+        store_tmem(EL + c * 32, lo);
+      }
+      tmem_st_wait();
+      fence_before_sync();
+      mbar_arrive(wk_done);
+      // ---- FFN: hidden slice j = relu(acc + b_in[j])  -> A operand of the matching FFN-out slice
+      for (int j = 0; j < 4; ++j) {
+        mbar_wait(&acc_full[1], accph[1]); accph[1] ^= 1;
+        fence_after_sync();
+        for (int c = 0; c < 4; ++c) {
+          load_acc(ACC1, c);
+          float b[32];
+          ld32(a.BIN + j * 128 + c * 32, b);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + b[i], 0.f);
+          publish(v, kKC);
+        }
+        if (j < 3) {
+          fence_before_sync();
+          mbar_arrive(wk_done);
+        }
+      }
+      // ---- final: y = LN3(e + acc + b_out) * mask   (layers.py:143-146)
+      mbar_wait(&acc_full[0], accph[0]); accph[0] ^= 1;
+      fence_after_sync();
+      sum = 0.f;
+      for (int c = 0; c < 4; ++c) {
+        float eh[32];
+        load_acc(EH, c);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) eh[i] = v[i];
+        load_acc(EL, c);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) eh[i] += v[i];
+        load_acc(ACC0, c);
+        float b[32];
+        ld32(a.BOUT + c * 32, b);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { v[i] = eh[i] + v[i] + b[i]; sum += v[i]; }
+        store_tmem(ACC0 + c * 32, v);
+      }
+      tmem_st_wait();
+      const float mean3 = sum * (1.f / 128.f);
+      var = 0.f;
+      for (int c = 0; c < 4; ++c) {
+        load_acc(ACC0, c);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { float d = v[i] - mean3; var += d * d; }
+      }
+      const float rstd3 = rsqrtf(var * (1.f / 128.f) + 1e-5f);
+      float* orow = a.out + ((size_t)rr * K + (in_range ? k : 0)) * 128;
+      for (int c = 0; c < 4; ++c) {
+        load_acc(ACC0, c);
+        float gm[32], bt[32];
+        ld32(a.LN3G + c * 32, gm);
+        ld32(a.LN3B + c * 32, bt);
+        if (in_range) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            float4 y;
+            int i = u * 4;
+            y.x = (matt != 0.f) ? (v[i + 0] - mean3) * rstd3 * gm[i + 0] + bt[i + 0] : 0.f;
+            y.y = (matt != 0.f) ? (v[i + 1] - mean3) * rstd3 * gm[i + 1] + bt[i + 1] : 0.f;
+            y.z = (matt != 0.f) ? (v[i + 2] - mean3) * rstd3 * gm[i + 2] + bt[i + 2] : 0.f;
+            y.w = (matt != 0.f) ? (v[i + 3] - mean3) * rstd3 * gm[i + 3] + bt[i + 3] : 0.f;
+            *reinterpret_cast<float4*>(orow + c * 32 + i) = y;
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown: all tensor-core work of this CTA has been consumed by its workers; in a cluster nobody may exit
+  //      while a peer can still multicast into its shared memory or arrive on its barriers
+  fence_before_sync();
+  __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();
+  if (warp == 4) tmem_dealloc<512>(tmem);
+}
+
+template <bool EDGE, int PASSES, int CLUSTER>
+static int launch(const Args& a, cudaStream_t stream) {
+  auto kern = edge_tc_kernel<EDGE, PASSES, CLUSTER>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTC);
+  if (e != cudaSuccess) {
+    snprintf(g_last_error, sizeof(g_last_error), "edge_tc_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  const long long R = (long long)a.S * a.G;
+  unsigned tiles = (unsigned)((R + 3) / 4);
+  tiles = (tiles + CLUSTER - 1) / CLUSTER * CLUSTER;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(tiles);
+  cfg.blockDim = dim3(kThreadsTC);
+  cfg.dynamicSmemBytes = kSmemTC;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, a);
+  if (e != cudaSuccess) {
+    snprintf(g_last_error, sizeof(g_last_error), "edge_tc_kernel: launch: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace pp
+
+using namespace pp;
+
+extern "C" int64_t pp_tc_stream_floats() { return tc::kStreamFloats; }
+
+// Tensor-core version of pp_ipmp_edge_node (path = 0) and pp_ipmp_edge_edge (path = 1).
+//   wstream: operand images of this layer and path, pp_tc_stream_floats() floats (weights.py: pack_tc_stream)
+//   passes : 3 = split TF32 (fp32-grade), 1 = plain TF32;  cluster: 1, 2 or 4 CTAs sharing the weight stream
+//   out    : accsum [S*G][128] (path 0) or hE_out [S*G][K][128] (path 1, may alias hE_in when he_shared == 0)
+extern "C" int pp_ipmp_edge_tc(const float* weights, int64_t layer, int64_t path, const float* wstream,
+                               const float* geo, const int32_t* nbr, const float* mask_attend, int64_t G, int64_t K,
+                               int64_t S, const float* hE_in, int64_t he_shared, const float* wsA, const float* wsN,
+                               const float* wsP, float* out, int64_t passes, int64_t cluster, cudaStream_t stream) {
+  PP_REQUIRE(weights && wstream && geo && nbr && mask_attend && hE_in && wsA && wsN && wsP && out, "null pointer");
+  PP_REQUIRE(layer >= 0 && layer < 3 && (path == 0 || path == 1), "layer / path out of range");
+  PP_REQUIRE(G > 0 && S > 0 && K > 0 && K <= PP_KMAX, "bad sizes");
+  PP_REQUIRE(passes == 1 || passes == 3, "passes must be 1 or 3");
+  PP_REQUIRE(cluster == 1 || cluster == 2 || cluster == 4, "cluster must be 1, 2 or 4");
+  const float* Lb = weights + layer * wl::kLayerStride;
+  tc::Args a{};
+  a.geo = geo; a.nbr = nbr; a.matt = mask_attend;
+  a.G = (int)G; a.K = (int)K; a.S = (int)S;
+  a.wstream = wstream;
+  a.B2 = Lb + (path ? PP_OFF(L0_E_B2) : PP_OFF(L0_N_B2));
+  a.B3 = Lb + PP_OFF(L0_E_B3);
+  a.LNG = Lb + PP_OFF(L0_LN2_G); a.LNB = Lb + PP_OFF(L0_LN2_B);
+  a.BIN = Lb + PP_OFF(L0_EF_BIN); a.BOUT = Lb + PP_OFF(L0_EF_BOUT);
+  a.LN3G = Lb + PP_OFF(L0_LN3_G); a.LN3B = Lb + PP_OFF(L0_LN3_B);
+  a.hE_in = hE_in; a.he_shared = (int)he_shared;
+  a.A = wsA; a.Nn = wsN; a.pglob = wsP;
+  a.out = out;
+  int rc;
+#define PP_TC_CASE(E, P, C) if (path == (E) && passes == (P) && cluster == (C)) rc = tc::launch<(E) != 0, P, C>(a, stream); else
+  PP_TC_CASE(0, 3, 1) PP_TC_CASE(0, 3, 2) PP_TC_CASE(0, 3, 4) PP_TC_CASE(0, 1, 1) PP_TC_CASE(0, 1, 2) PP_TC_CASE(0, 1, 4)
+  PP_TC_CASE(1, 3, 1) PP_TC_CASE(1, 3, 2) PP_TC_CASE(1, 3, 4) PP_TC_CASE(1, 1, 1) PP_TC_CASE(1, 1, 2) PP_TC_CASE(1, 1, 4)
+  rc = 2;
+#undef PP_TC_CASE
+  if (rc) return rc;
+  return check_launch("pp_ipmp_edge_tc");
+}

@@ -7,7 +7,7 @@ import numpy as np
 import torch
 
 from . import _lib, tables
-from .weights import pack_weights
+from .weights import pack_tc_stream, pack_weights
 
 SIGMA_MIN, SIGMA_MAX = 0.01 * np.pi, np.pi  # schedule.py:148-149 defaults
 TOP_K = 32
@@ -96,13 +96,23 @@ class Workspace:
 class Engine:
     """Packed weights + kernels for one device."""
 
-    def __init__(self, state_dict, device):
+    # precision / execution modes of the per-edge message MLPs
+    #   fp32   CUDA-core FFMA kernels (csrc/mpnn.cu), exact fp32
+    #   tf32x3 tcgen05 tensor cores, split-TF32 (3 MMAs per product, fp32-grade): parity mode of the tensor path
+    #   tf32   tcgen05 tensor cores, plain TF32: fast mode with a looser stated tolerance
+    MODES = ("fp32", "tf32x3", "tf32")
+
+    def __init__(self, state_dict, device, mode="tf32x3", cluster=1):
+        if mode not in self.MODES:
+            raise ValueError(f"mode must be one of {self.MODES}")
+        self.mode, self.cluster = mode, int(cluster)
         self.dev = torch.device(device)
         if self.dev.type != "cuda":
             raise RuntimeError("packppi_b200 runs on CUDA devices only; there is no CPU fallback "
                                "(use the reference implementation for --device cpu)")
         layout, total = _lib.layout()
         self.wblob = pack_weights(state_dict, layout, total).to(self.dev)
+        self.wtc = pack_tc_stream(state_dict, _lib.load().pp_tc_stream_floats()).to(self.dev)
         self.tables = DeviceTables.get(self.dev)
         self._ws = {}
 
@@ -137,20 +147,29 @@ class Engine:
             first = layer == 0
             hE_in, shared, edge = (hE0 if first else ws.hE), (1 if first else 0), layer < 2
             common = (graph.geo, graph.nbr, graph.mask_attend)
-            if _lib.PROFILE is None:
+            size = (graph.mask, G, K, S)
+            if self.mode == "fp32" and _lib.PROFILE is None:
                 _lib.call("pp_ipmp_layer", W, layer, *common, graph.msum, graph.mask, G, K, S, ws.hV, hE_in, shared,
                           ws.hE, 1 if edge else 0, ws.wsA, ws.wsN, ws.wsP, ws.wsAcc, kernels=5 if edge else 3)
                 continue
-            # instrumented mode: the same five kernels through their own entry points
-            size = (graph.mask, G, K, S)
+            tcp = (3 if self.mode == "tf32x3" else 1, self.cluster)
+            # the five kernels of a layer through their own entry points (instrumented fp32 mode, tensor-core modes)
             _lib.call("pp_ipmp_node_pre", W, layer, 0, *common, *size, ws.hV, ws.wsA, ws.wsN, ws.wsP, rows=S * G)
-            _lib.call("pp_ipmp_edge_node", W, layer, *common, *size, hE_in, shared, ws.wsA, ws.wsN, ws.wsP, ws.wsAcc,
-                      rows=S * G)
+            if self.mode == "fp32":
+                _lib.call("pp_ipmp_edge_node", W, layer, *common, *size, hE_in, shared, ws.wsA, ws.wsN, ws.wsP,
+                          ws.wsAcc, rows=S * G)
+            else:
+                _lib.call("pp_ipmp_edge_tc", W, layer, 0, self.wtc[layer, 0], *common, G, K, S, hE_in, shared, ws.wsA,
+                          ws.wsN, ws.wsP, ws.wsAcc, *tcp, rows=S * G, tag="node")
             _lib.call("pp_ipmp_node_post", W, layer, *common, graph.msum, *size, ws.wsAcc, ws.hV, rows=S * G)
             if edge:
                 _lib.call("pp_ipmp_node_pre", W, layer, 1, *common, *size, ws.hV, ws.wsA, ws.wsN, ws.wsP, rows=S * G)
-                _lib.call("pp_ipmp_edge_edge", W, layer, *common, *size, hE_in, shared, ws.wsA, ws.wsN, ws.wsP, ws.hE,
-                          rows=S * G)
+                if self.mode == "fp32":
+                    _lib.call("pp_ipmp_edge_edge", W, layer, *common, *size, hE_in, shared, ws.wsA, ws.wsN, ws.wsP,
+                              ws.hE, rows=S * G)
+                else:
+                    _lib.call("pp_ipmp_edge_tc", W, layer, 1, self.wtc[layer, 1], *common, G, K, S, hE_in, shared,
+                              ws.wsA, ws.wsN, ws.wsP, ws.hE, *tcp, rows=S * G, tag="edge")
         return ws.hV
 
     def network(self, graph, batch, chi, t):

@@ -151,3 +151,51 @@ def pack_weights(sd, layout, total_floats):
     put("RBF_MU", torch.linspace(0.0, 20.0, 16))  # encoder.py:122-123
     put("TIME_FREQ", torch.exp(torch.arange(8, dtype=torch.float32) * -(math.log(10000) / 7)))  # layers.py:260-262
     return blob
+
+
+def _tf32_split(w):
+    """w = hi + lo exactly, hi representable in TF32 (low 13 mantissa bits cleared)."""
+    hi = (w.contiguous().view(torch.int32) & -8192).view(torch.float32)
+    return hi, w - hi
+
+
+def _umma_image(w):
+    """[128 rows, kc] K-major operand -> flat image in the no-swizzle core-matrix layout of csrc/umma.cuh:
+    float offset(row, k) = (k // 4) * 512 + (row // 8) * 32 + (row % 8) * 4 + k % 4."""
+    rows, kc = w.shape
+    assert rows == 128 and kc % 4 == 0
+    return w.reshape(16, 8, kc // 4, 4).permute(2, 0, 1, 3).contiguous().reshape(-1)
+
+
+def pack_tc_stream(sd, stream_floats):
+    """Operand images for the tensor-core edge kernels (csrc/mpnn_tc.cu): [3 layers, 2 paths, stream_floats].
+
+    Per (layer, path) the chunks follow the kernel's consumption order, each chunk = hi image then lo image:
+      G1: W_in[:, h_E | pair geometry]  k = 0..167 in chunks of 32, 32, 32, 32, 32, 8
+      G2: W_inter.0 (4 chunks), G3: W_out (4 chunks)
+      for j in 0..3:  FFN-in rows 128j..128j+127 (4 chunks), FFN-out columns 128j..128j+127 (4 chunks)
+    The node path (path 0) uses G1 and G2 of node_message_fn only; the rest of its stream is zero."""
+    check_state_dict(sd)
+    f = {k: v.detach().to("cpu", torch.float32) for k, v in sd.items()}
+    out = torch.zeros(N_LAYERS, 2, stream_floats, dtype=torch.float32)
+    for l in range(N_LAYERS):
+        p = f"mpnn.mpnn_layers.{l}."
+        for path, fn in enumerate(("node_message_fn", "edge_message_fn")):
+            Win = f[p + fn + ".W_in.weight"]
+            mats = [torch.cat([Win[:, 128:256], Win[:, 416:456]], 1), f[p + fn + ".W_inter.0.weight"]]
+            if path == 1:
+                mats.append(f[p + fn + ".W_out.weight"])
+                Fi, Fo = f[p + "edge_dense.W_in.weight"], f[p + "edge_dense.W_out.weight"]
+                for j in range(4):
+                    mats.append(Fi[128 * j:128 * (j + 1), :])
+                    mats.append(Fo[:, 128 * j:128 * (j + 1)])
+            pieces = []
+            for M in mats:
+                for k0 in range(0, M.shape[1], 32):
+                    kc = min(32, M.shape[1] - k0)
+                    hi, lo = _tf32_split(M[:, k0:k0 + kc])
+                    pieces += [_umma_image(hi), _umma_image(lo)]
+            flat = torch.cat(pieces)
+            assert flat.numel() <= stream_floats
+            out[l, path, :flat.numel()] = flat
+    return out
