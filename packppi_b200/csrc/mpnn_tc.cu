@@ -4,12 +4,13 @@
 // split (only the 168-wide [h_E | pair geometry] part of the first Linear is per edge).  One CTA = one tile of 128
 // edges (4 residues x 32 neighbours) = the M dimension of a 128 x 128 UMMA; the whole GEMM chain of the tile stays on
 // chip:
-//   warps 0-3  row workers: thread = edge row = TMEM lane.  Build the first A operand, then act as the epilogue of
-//              every GEMM: tcgen05.ld 32 columns -> bias / ReLU / LayerNorm (a row is thread-private, no shuffles) ->
-//              next A operand, written 32 columns at a time into a shared-memory ring (or into TMEM for the FFN input)
-//   warp 4     MMA issuer (one elected lane): tcgen05.mma kind::tf32, accumulators ping-pong between two 128-column
+//   warps 0-7  row workers, two groups of 128 threads: thread (group, m) owns edge row m = TMEM lane m and two of the
+//              four 32-column chunks.  They build the first A operand, then act as the epilogue of every GEMM:
+//              tcgen05.ld 32 columns -> bias / ReLU / LayerNorm -> next A operand, written into a shared-memory ring
+//              (or into TMEM for the FFN input); gathered rows are fetched before the wait on the accumulator
+//   warp 8     MMA issuer (one elected lane): tcgen05.mma kind::tf32, accumulators ping-pong between two 128-column
 //              TMEM regions, completion signalled with tcgen05.commit on mbarriers
-//   warp 5     weight loader: cp.async.bulk of pre-packed operand images (K-major core-matrix layout, consumption
+//   warp 9     weight loader: cp.async.bulk of pre-packed operand images (K-major core-matrix layout, consumption
 //              order, see pack_tc_stream in packppi_b200/weights.py) into a ring; with CLUSTER > 1 every CTA fetches
 //              1/CLUSTER of each image and multicasts it to the whole cluster, dividing the L2 -> SM weight traffic
 // A chunks are consumed by the MMA warp as soon as they are written, so the epilogue of GEMM n overlaps the MMAs of
@@ -29,11 +30,15 @@ using namespace umma;
 
 constexpr int kRows = 128;
 constexpr int kKC = 32;
-constexpr int kSA = 3, kSB = 3;
+constexpr int kSA = 2;   // A ring: slots of 32 k-columns (hi + lo images, 32 KB)
+constexpr int kSB = 8;   // B ring: sub-slots of 16 k-columns (hi + lo images, 16 KB): deep, to cover the L2 latency
 constexpr int kImgFloats = kRows * kKC;          // one operand image (hi or lo) of a 32-column chunk
 constexpr uint32_t kImgBytes = kImgFloats * 4;   // 16 KB
 constexpr int kSlotFloats = 2 * kImgFloats;      // hi + lo
-constexpr int kThreadsTC = 192;
+constexpr int kSubK = 16;                        // k-columns per B sub-slot
+constexpr int kSubImgFloats = kRows * kSubK;     // 8 KB image
+constexpr int kSubFloats = 2 * kSubImgFloats;
+constexpr int kThreadsTC = 320;  // 8 worker warps (two groups of 128 rows), MMA warp, loader warp
 constexpr uint32_t kLbo = kRows * 16, kSbo = 128;
 constexpr uint32_t kIdesc = idesc_tf32(128, 128);
 
@@ -42,7 +47,12 @@ constexpr int kChunksEdge = 6 + 4 + 4 + 4 * 8;   // + G3, 4 x (FFN-in slice, FFN
 constexpr long long kStreamFloats = 2LL * 128 * (168 + 128 + 128 + 4 * 256);
 
 constexpr size_t kBarBytes = (2 * kSA + 2 * kSB + 2 + 1) * 8;
-constexpr size_t kSmemTC = (size_t)(kSA + kSB) * kSlotFloats * 4 + kBarBytes + 16;
+// per-column parameters staged in shared memory (floats): b2, b3, LN2 gain/bias, FFN b_in (512), b_out, LN3 gain/bias
+constexpr int kP_B2 = 0, kP_B3 = 128, kP_LN2G = 256, kP_LN2B = 384, kP_BIN = 512, kP_BOUT = 1024, kP_LN3G = 1152,
+              kP_LN3B = 1280, kParamFloats = 1408;
+constexpr int kRedFloats = 4 * 2 * 128;  // four row reductions x two groups
+constexpr size_t kSmemTC = ((size_t)kSA * kSlotFloats + (size_t)kSB * kSubFloats) * 4 + kBarBytes + 16 +
+                           (kParamFloats + kRedFloats) * 4;
 
 struct Args {
   const float* geo; const int* nbr; const float* matt;
@@ -114,7 +124,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   float* Aring = reinterpret_cast<float*>(smem);
   float* Bring = Aring + kSA * kSlotFloats;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Bring + kSB * kSlotFloats);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Bring + kSB * kSubFloats);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kSA;
   uint64_t* b_full = a_empty + kSA;
@@ -122,10 +132,15 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
   uint64_t* acc_full = b_empty + kSB;  // [2]
   uint64_t* wk_done = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wk_done + 1);
+  float* prm = reinterpret_cast<float*>(wk_done + 3);
+  float* red = prm + kParamFloats;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int R = a.S * a.G, K = a.K;
-  const int rb = blockIdx.x * 4;
+  const int ntiles = (R + 3) / 4;
+  // persistent CTAs: every CTA runs the same number of iterations (a cluster shares one weight stream in lockstep);
+  // iterations past the last tile work on fully masked rows
+  const int niter = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
   constexpr int NCHUNK = EDGE ? kChunksEdge : kChunksNode;
   constexpr uint16_t kMask = (uint16_t)((1u << CLUSTER) - 1);
 
@@ -134,10 +149,17 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
     for (int i = 0; i < kSB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], CLUSTER); }
     mbar_init(&acc_full[0], 1);
     mbar_init(&acc_full[1], 1);
-    mbar_init(wk_done, 128);
+    mbar_init(wk_done, 256);
     mbar_fence_init();
   }
-  if (warp == 4) tmem_alloc<512>(tmem_slot);
+  {  // stage the per-column parameters
+    const float* src[8] = {a.B2, a.B3, a.LNG, a.LNB, a.BIN, a.BOUT, a.LN3G, a.LN3B};
+    const int off[9] = {kP_B2, kP_B3, kP_LN2G, kP_LN2B, kP_BIN, kP_BOUT, kP_LN3G, kP_LN3B, kParamFloats};
+    for (int t = 0; t < 8; ++t)
+      if (EDGE || t == 0)
+        for (int i = tid; i < off[t + 1] - off[t]; i += kThreadsTC) prm[off[t] + i] = src[t][i];
+  }
+  if (warp == 8) tmem_alloc<512>(tmem_slot);
   fence_before_sync();
   __syncthreads();
   if (CLUSTER > 1) cluster_sync_all();  // every CTA's barriers exist before any remote arrive / multicast
@@ -145,96 +167,120 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
   const uint32_t tmem = *tmem_slot;
   const uint32_t ACC0 = tmem, ACC1 = tmem + 128, EH = tmem + 256, EL = tmem + 384;
 
-  if (warp == 5) {
+  if (warp == 9) {
     // ------------------------------------------------------------------ weight loader
     if (lane == 0) {
       Ring rb_{0, 1};
-      const float* src = a.wstream;
       const uint32_t crank = (CLUSTER > 1) ? cluster_rank() : 0;
-      for (int i = 0; i < NCHUNK; ++i) {
-        const int kc = (i == 5) ? 8 : kKC;
-        const uint32_t img = (uint32_t)kRows * kc * 4;
-        mbar_wait(&b_empty[rb_.idx], rb_.phase);
-        mbar_arrive_expect_tx(&b_full[rb_.idx], img * (PASSES == 3 ? 2 : 1));
-        float* dst = Bring + rb_.idx * kSlotFloats;
-        if (CLUSTER == 1) {
-          bulk_g2s(dst, src, img, &b_full[rb_.idx]);
-          if (PASSES == 3) bulk_g2s(dst + kImgFloats, src + kRows * kc, img, &b_full[rb_.idx]);
-        } else {
-          const uint32_t piece = img / CLUSTER, po = crank * piece / 4;
-          bulk_g2s_mc(dst + po, src + po, piece, &b_full[rb_.idx], kMask);
-          if (PASSES == 3) bulk_g2s_mc(dst + kImgFloats + po, src + kRows * kc + po, piece, &b_full[rb_.idx], kMask);
+      for (int it = 0; it < niter; ++it) {
+        const float* src = a.wstream;
+        for (int i = 0; i < NCHUNK; ++i) {
+          const int kc = (i == 5) ? 8 : kKC;
+          for (int h = 0; h * kSubK < kc; ++h) {
+            const int kcs = min(kSubK, kc - h * kSubK);
+            const uint32_t img = (uint32_t)kRows * kcs * 4;
+            const float* shi = src + h * kSubImgFloats;
+            const float* slo = src + kRows * kc + h * kSubImgFloats;
+            mbar_wait(&b_empty[rb_.idx], rb_.phase);
+            mbar_arrive_expect_tx(&b_full[rb_.idx], img * (PASSES == 3 ? 2 : 1));
+            float* dst = Bring + rb_.idx * kSubFloats;
+            if (CLUSTER == 1) {
+              bulk_g2s(dst, shi, img, &b_full[rb_.idx]);
+              if (PASSES == 3) bulk_g2s(dst + kSubImgFloats, slo, img, &b_full[rb_.idx]);
+            } else {
+              const uint32_t piece = img / CLUSTER, po = crank * piece / 4;
+              bulk_g2s_mc(dst + po, shi + po, piece, &b_full[rb_.idx], kMask);
+              if (PASSES == 3) bulk_g2s_mc(dst + kSubImgFloats + po, slo + po, piece, &b_full[rb_.idx], kMask);
+            }
+            rb_.next(kSB);
+          }
+          src += 2 * kRows * kc;
         }
-        src += 2 * kRows * kc;
-        rb_.next(kSB);
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       Ring ra{0, 0}, rbq{0, 0};
       uint32_t wk_phase = 0;
       auto chunk = [&](bool ss, uint32_t acc, uint32_t a_col, int kc, bool fresh) {
         if (ss) mbar_wait(&a_full[ra.idx], ra.phase);
-        mbar_wait(&b_full[rbq.idx], rbq.phase);
-        fence_after_sync();
-        const uint32_t as = smem_u32(Aring + ra.idx * kSlotFloats), bs = smem_u32(Bring + rbq.idx * kSlotFloats);
+        const uint32_t as = smem_u32(Aring + ra.idx * kSlotFloats);
+        for (int h = 0; h * kSubK < kc; ++h) {
+          const int kcs = min(kSubK, kc - h * kSubK);
+          mbar_wait(&b_full[rbq.idx], rbq.phase);
+          fence_after_sync();
+          const uint32_t bs = smem_u32(Bring + rbq.idx * kSubFloats);
 #pragma unroll
-        for (int p = 0; p < PASSES; ++p) {
-          const uint32_t ao = (p == 2) ? kImgBytes : 0, bo = (p == 1) ? kImgBytes : 0;
-          for (int kk = 0; kk < kc; kk += 8) {
-            const uint64_t bd = smem_desc(bs + bo + (kk / 4) * kLbo, kLbo, kSbo);
-            const uint32_t accum = (fresh && p == 0 && kk == 0) ? 0u : 1u;
-            if (ss) mma_tf32_ss(acc, smem_desc(as + ao + (kk / 4) * kLbo, kLbo, kSbo), bd, kIdesc, accum);
-            else mma_tf32_ts(acc, ((p == 2) ? EL : EH) + a_col + kk, bd, kIdesc, accum);
+          for (int p = 0; p < PASSES; ++p) {
+            const uint32_t ao = (p == 2) ? kImgBytes : 0, bo = (p == 1) ? (uint32_t)kSubImgFloats * 4 : 0;
+            for (int kk = 0; kk < kcs; kk += 8) {
+              const uint64_t bd = smem_desc(bs + bo + (kk / 4) * kLbo, kLbo, kSbo);
+              const uint32_t accum = (fresh && h == 0 && p == 0 && kk == 0) ? 0u : 1u;
+              if (ss) mma_tf32_ss(acc, smem_desc(as + ao + (h * 4 + kk / 4) * kLbo, kLbo, kSbo), bd, kIdesc, accum);
+              else mma_tf32_ts(acc, ((p == 2) ? EL : EH) + a_col + h * kSubK + kk, bd, kIdesc, accum);
+            }
           }
+          if (CLUSTER == 1) mma_commit(&b_empty[rbq.idx]); else mma_commit_mc(&b_empty[rbq.idx], kMask);
+          rbq.next(kSB);
         }
-        if (CLUSTER == 1) mma_commit(&b_empty[rbq.idx]); else mma_commit_mc(&b_empty[rbq.idx], kMask);
-        rbq.next(kSB);
         if (ss) { mma_commit(&a_empty[ra.idx]); ra.next(kSA); }
       };
-      // G1: [h_E | pair] (168) -> ACC0
-      for (int c = 0; c < 6; ++c) chunk(true, ACC0, 0, c == 5 ? 8 : kKC, c == 0);
-      mma_commit(&acc_full[0]);
-      // G2 -> ACC1
-      for (int c = 0; c < 4; ++c) chunk(true, ACC1, 0, kKC, c == 0);
-      mma_commit(&acc_full[1]);
-      if (EDGE) {
-        // G3 -> ACC0
-        for (int c = 0; c < 4; ++c) chunk(true, ACC0, 0, kKC, c == 0);
+      for (int it = 0; it < niter; ++it) {
+        // G1: [h_E | pair] (168) -> ACC0
+        for (int c = 0; c < 6; ++c) chunk(true, ACC0, 0, c == 5 ? 8 : kKC, c == 0);
         mma_commit(&acc_full[0]);
-        for (int j = 0; j < 4; ++j) {
-          mbar_wait(wk_done, wk_phase);  // e is in TMEM (j = 0) / ACC1 has been drained (j > 0)
-          wk_phase ^= 1;
-          fence_after_sync();
-          for (int c = 0; c < 4; ++c) chunk(false, ACC1, c * kKC, kKC, c == 0);  // FFN-in slice j: A = e from TMEM
-          mma_commit(&acc_full[1]);
-          for (int c = 0; c < 4; ++c) chunk(true, ACC0, 0, kKC, j == 0 && c == 0);  // FFN-out slice j accumulates
+        // G2 -> ACC1
+        for (int c = 0; c < 4; ++c) chunk(true, ACC1, 0, kKC, c == 0);
+        mma_commit(&acc_full[1]);
+        if (EDGE) {
+          // G3 -> ACC0
+          for (int c = 0; c < 4; ++c) chunk(true, ACC0, 0, kKC, c == 0);
+          mma_commit(&acc_full[0]);
+          for (int j = 0; j < 4; ++j) {
+            mbar_wait(wk_done, wk_phase);  // e is in TMEM (j = 0) / ACC1 has been drained (j > 0)
+            wk_phase ^= 1;
+            fence_after_sync();
+            for (int c = 0; c < 4; ++c) chunk(false, ACC1, c * kKC, kKC, c == 0);  // FFN-in slice j: A = e from TMEM
+            mma_commit(&acc_full[1]);
+            for (int c = 0; c < 4; ++c) chunk(true, ACC0, 0, kKC, j == 0 && c == 0);  // FFN-out slice j accumulates
+          }
+          mma_commit(&acc_full[0]);
         }
-        mma_commit(&acc_full[0]);
+        // the workers have drained both accumulators of this tile before the next tile's G1 overwrites them
+        mbar_wait(wk_done, wk_phase);
+        wk_phase ^= 1;
+        fence_after_sync();
       }
     }
   } else {
-    // ------------------------------------------------------------------ row workers (thread = edge row = TMEM lane)
-    const int m = tid, rl = warp, k = lane;
+    // ------------------------------------------------------------------ row workers
+    // Two groups of 128 threads; thread (grp, m) owns edge row m (= TMEM lane m) and the column chunks {grp, grp + 2}
+    // of every 128-wide activation, so consecutive A chunks are produced by alternating groups.
+    const int grp = tid >> 7, m = tid & 127, rl = m >> 5, k = lane;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t accph[2] = {0, 0};
+    int qbase = 0;  // running A-chunk counter (ring position persists across tiles)
+    for (int it = 0; it < niter; ++it) {
+    const int rb = (it * (int)gridDim.x + (int)blockIdx.x) * 4;
     const int r = rb + rl;
     const bool in_range = r < R && k < K;
     const int rr = min(r, R - 1);
     const int s = rr / a.G, g = rr - s * a.G;
     const float matt = in_range ? a.matt[(size_t)g * K + k] : 0.f;
+    const bool on = matt != 0.f;
     const int jrow = in_range ? s * a.G + a.nbr[(size_t)g * K + k] : rr;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     const float* hrow = a.hE_in + ((size_t)(a.he_shared ? g : rr) * K + (in_range ? k : 0)) * 128;
-    Ring pa{0, 1};
-    uint32_t accph[2] = {0, 0};
     float v[32];
 
-    auto publish = [&](const float* vals, int kc) {
-      mbar_wait(&a_empty[pa.idx], pa.phase);
-      put_chunk<PASSES>(Aring + pa.idx * kSlotFloats, m, vals, kc);
+    // A chunk number q of the tile's fixed schedule -> ring slot q % kSA, (q / kSA)-th use of that slot
+    auto publish = [&](int qrel, const float* vals, int kc) {
+      const int q = qbase + qrel;
+      const int slot = q % kSA;
+      mbar_wait(&a_empty[slot], ((q / kSA) & 1) ^ 1);
+      put_chunk<PASSES>(Aring + slot * kSlotFloats, m, vals, kc);
       fence_async_smem();
-      mbar_arrive(&a_full[pa.idx]);
-      pa.next(kSA);
+      mbar_arrive(&a_full[slot]);
     };
     auto load_acc = [&](uint32_t acc, int c) {
       uint32_t u[32];
@@ -249,55 +295,75 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
       for (int i = 0; i < 32; ++i) u[i] = __float_as_uint(vals[i]);
       tmem_st32(col + lane_base, u);
     };
+    auto row_total = [&](float partial, int which) -> float {  // sum over the two threads that share a row
+      red[(which * 2 + grp) * 128 + m] = partial;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      return red[(which * 2) * 128 + m] + red[(which * 2 + 1) * 128 + m];
+    };
 
-    // ---- first A operand: h_E row (4 chunks) and the pair geometry (32 + 8 columns)   (layers.py:93-115)
-    for (int c = 0; c < 4; ++c) {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        float4 x = in_range ? *reinterpret_cast<const float4*>(hrow + c * 32 + u * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        v[u * 4] = x.x; v[u * 4 + 1] = x.y; v[u * 4 + 2] = x.z; v[u * 4 + 3] = x.w;
-      }
-      publish(v, kKC);
-    }
+    // ---- first A operand: h_E row (chunks 0-3) and the pair geometry (chunk 4: 32 columns, chunk 5: 8 columns)
     {
+      float4 h[2][8];
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          h[t][u] = in_range ? *reinterpret_cast<const float4*>(hrow + (grp + 2 * t) * 32 + u * 4)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
       const float* fr = a.geo + (size_t)g * PP_GEO_STRIDE;
       const float* pi = a.pglob + (size_t)rr * 24;
       const float* pj = a.pglob + (size_t)jrow * 24;
-      float ng[8];
+      float geo[32];
 #pragma unroll
       for (int pt = 0; pt < 8; ++pt) {
         float jx = pj[pt * 3], jy = pj[pt * 3 + 1], jz = pj[pt * 3 + 2];
-        float dx = jx - fr[9], dy = jy - fr[10], dz = jz - fr[11];
-        float qx = fr[0] * dx + fr[3] * dy + fr[6] * dz;
-        float qy = fr[1] * dx + fr[4] * dy + fr[7] * dz;
-        float qz = fr[2] * dx + fr[5] * dy + fr[8] * dz;
-        float gx = pi[pt * 3] - jx, gy = pi[pt * 3 + 1] - jy, gz = pi[pt * 3 + 2] - jz;
-        v[pt * 3] = qx; v[pt * 3 + 1] = qy; v[pt * 3 + 2] = qz;
-        v[24 + pt] = sqrtf(qx * qx + qy * qy + qz * qz + 1e-8f);
-        ng[pt] = sqrtf(gx * gx + gy * gy + gz * gz + 1e-8f);
+        if (grp == 0) {  // neighbour points in the local frame and their norms   (layers.py:93-97)
+          float dx = jx - fr[9], dy = jy - fr[10], dz = jz - fr[11];
+          float qx = fr[0] * dx + fr[3] * dy + fr[6] * dz;
+          float qy = fr[1] * dx + fr[4] * dy + fr[7] * dz;
+          float qz = fr[2] * dx + fr[5] * dy + fr[8] * dz;
+          geo[pt * 3] = qx; geo[pt * 3 + 1] = qy; geo[pt * 3 + 2] = qz;
+          geo[24 + pt] = sqrtf(qx * qx + qy * qy + qz * qz + 1e-8f);
+        } else {         // distances between the global points   (layers.py:99-103)
+          float gx = pi[pt * 3] - jx, gy = pi[pt * 3 + 1] - jy, gz = pi[pt * 3 + 2] - jz;
+          geo[pt] = sqrtf(gx * gx + gy * gy + gz * gz + 1e-8f);
+        }
       }
-      publish(v, kKC);
-      publish(ng, 8);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { v[u * 4] = h[t][u].x; v[u * 4 + 1] = h[t][u].y; v[u * 4 + 2] = h[t][u].z; v[u * 4 + 3] = h[t][u].w; }
+        publish(grp + 2 * t, v, kKC);
+      }
+      if (grp == 0) publish(4, geo, kKC); else publish(5, geo, 8);
     }
 
-    // ---- epilogue of G1: x1 = relu(acc + A_i + N_j)
-    mbar_wait(&acc_full[0], accph[0]); accph[0] ^= 1;
-    fence_after_sync();
+    // ---- epilogue of G1: x1 = relu(acc + A_i + N_j); the two gathered rows are fetched before the wait
     {
       const float* Ai = a.A + (size_t)rr * 128;
       const float* Nj = a.Nn + (size_t)jrow * 128;
-      for (int c = 0; c < 4; ++c) {
-        load_acc(ACC0, c);
+      float4 an[2][8];
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          float4 x = *reinterpret_cast<const float4*>(Ai + c * 32 + u * 4);
-          float4 y = *reinterpret_cast<const float4*>(Nj + c * 32 + u * 4);
-          v[u * 4 + 0] = fmaxf(v[u * 4 + 0] + x.x + y.x, 0.f);
-          v[u * 4 + 1] = fmaxf(v[u * 4 + 1] + x.y + y.y, 0.f);
-          v[u * 4 + 2] = fmaxf(v[u * 4 + 2] + x.z + y.z, 0.f);
-          v[u * 4 + 3] = fmaxf(v[u * 4 + 3] + x.w + y.w, 0.f);
+          float4 x = *reinterpret_cast<const float4*>(Ai + (grp + 2 * t) * 32 + u * 4);
+          float4 y = *reinterpret_cast<const float4*>(Nj + (grp + 2 * t) * 32 + u * 4);
+          an[t][u] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
         }
-        publish(v, kKC);
+      mbar_wait(&acc_full[0], accph[0]); accph[0] ^= 1;
+      fence_after_sync();
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        load_acc(ACC0, grp + 2 * t);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          v[u * 4 + 0] = fmaxf(v[u * 4 + 0] + an[t][u].x, 0.f);
+          v[u * 4 + 1] = fmaxf(v[u * 4 + 1] + an[t][u].y, 0.f);
+          v[u * 4 + 2] = fmaxf(v[u * 4 + 2] + an[t][u].z, 0.f);
+          v[u * 4 + 3] = fmaxf(v[u * 4 + 3] + an[t][u].w, 0.f);
+        }
+        publish(6 + grp + 2 * t, v, kKC);
       }
     }
     // ---- epilogue of G2: x2 = relu(acc + b2)
@@ -305,13 +371,14 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
     fence_after_sync();
     if (!EDGE) {
       // node path: masked sum over the 32 edges of the residue (= the 32 lanes of this warp), layers.py:125-127
-      for (int c = 0; c < 4; ++c) {
-        load_acc(ACC1, c);
-        float b[32];
-        ld32(a.B2 + c * 32, b);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = (matt != 0.f) ? fmaxf(v[i] + b[i], 0.f) : 0.f;
-        // transpose-reduce: after the 5 steps lane l holds the column sum of column l
+      for (int t = 0; t < 2; ++t) {
+        const int c = grp + 2 * t;
+        load_acc(ACC1, c);
+        const float* b = prm + kP_B2 + c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = on ? fmaxf(v[i] + b[i], 0.f) : 0.f;
+        // transpose-reduce: after the 5 steps lane l holds the sum of column l over the 32 lanes
 #pragma unroll
         for (int step = 16; step >= 1; step >>= 1) {
           const bool upper = (lane & step) != 0;
@@ -325,71 +392,85 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
         if (r < R) a.out[(size_t)r * 128 + c * 32 + lane] = v[0];
       }
     } else {
-      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int c = grp + 2 * t;
         load_acc(ACC1, c);
-        float b[32];
-        ld32(a.B2 + c * 32, b);
+        const float* b = prm + kP_B2 + c * 32;
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + b[i], 0.f);
-        publish(v, kKC);
+        publish(10 + c, v, kKC);
       }
       // ---- epilogue of G3: e = LN2(h_E + mask * (acc + b3))   (layers.py:139-142); e -> TMEM as (hi, lo)
-      mbar_wait(&acc_full[0], accph[0]); accph[0] ^= 1;
-      fence_after_sync();
-      float sum = 0.f;
-      for (int c = 0; c < 4; ++c) {
-        load_acc(ACC0, c);
-        float b[32];
-        ld32(a.B3 + c * 32, b);
+      {
+        float4 h[2][8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          float4 h = in_range ? *reinterpret_cast<const float4*>(hrow + c * 32 + u * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float hh[4] = {h.x, h.y, h.z, h.w};
+        for (int t = 0; t < 2; ++t)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            int i = u * 4 + q;
-            v[i] = hh[q] + ((matt != 0.f) ? v[i] + b[i] : 0.f);
-            sum += v[i];
+          for (int u = 0; u < 8; ++u)
+            h[t][u] = in_range ? *reinterpret_cast<const float4*>(hrow + (grp + 2 * t) * 32 + u * 4)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        mbar_wait(&acc_full[0], accph[0]); accph[0] ^= 1;
+        fence_after_sync();
+        float sum = 0.f;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int c = grp + 2 * t;
+          load_acc(ACC0, c);
+          const float* b = prm + kP_B3 + c * 32;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float hh[4] = {h[t][u].x, h[t][u].y, h[t][u].z, h[t][u].w};
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const int i = u * 4 + q4;
+              v[i] = hh[q4] + (on ? v[i] + b[i] : 0.f);
+              sum += v[i];
+            }
           }
+          store_tmem(ACC0 + c * 32, v);
         }
-        store_tmem(ACC0 + c * 32, v);
-      }
-      tmem_st_wait();
-      const float mean = sum * (1.f / 128.f);
-      float var = 0.f;
-      for (int c = 0; c < 4; ++c) {
-        load_acc(ACC0, c);
+        tmem_st_wait();
+        const float mean = row_total(sum, 0) * (1.f / 128.f);
+        float var = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { float d = v[i] - mean; var += d * d; }
-      }
-      const float rstd = rsqrtf(var * (1.f / 128.f) + 1e-5f);
-      for (int c = 0; c < 4; ++c) {
-        load_acc(ACC0, c);
-        float lo[32], gm[32];
-        ld32(a.LNG + c * 32, gm);
-        ld32(a.LNB + c * 32, lo);
+        for (int t = 0; t < 2; ++t) {
+          load_acc(ACC0, grp + 2 * t);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float e = (v[i] - mean) * rstd * gm[i] + lo[i];
-          split_tf32(e, v[i], lo[i]);
+          for (int i = 0; i < 32; ++i) { float d = v[i] - mean; var += d * d; }
         }
-        store_tmem(EH + c * 32, v);
-        store_tmem(EL + c * 32, lo);
+        const float rstd = rsqrtf(row_total(var, 1) * (1.f / 128.f) + 1e-5f);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int c = grp + 2 * t;
+          load_acc(ACC0, c);
+          const float* gm = prm + kP_LN2G + c * 32;
+          const float* bt = prm + kP_LN2B + c * 32;
+          float lo[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float e = (v[i] - mean) * rstd * gm[i] + bt[i];
+            split_tf32(e, v[i], lo[i]);
+          }
+          store_tmem(EH + c * 32, v);
+          store_tmem(EL + c * 32, lo);
+        }
+        tmem_st_wait();
+        fence_before_sync();
+        mbar_arrive(wk_done);
       }
-      tmem_st_wait();
-      fence_before_sync();
-      mbar_arrive(wk_done);
       // ---- FFN: hidden slice j = relu(acc + b_in[j])  -> A operand of the matching FFN-out slice
       for (int j = 0; j < 4; ++j) {
         mbar_wait(&acc_full[1], accph[1]); accph[1] ^= 1;
         fence_after_sync();
-        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int c = grp + 2 * t;
           load_acc(ACC1, c);
-          float b[32];
-          ld32(a.BIN + j * 128 + c * 32, b);
+          const float* b = prm + kP_BIN + j * 128 + c * 32;
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + b[i], 0.f);
-          publish(v, kKC);
+          publish(14 + 4 * j + c, v, kKC);
         }
         if (j < 3) {
           fence_before_sync();
@@ -399,8 +480,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
       // ---- final: y = LN3(e + acc + b_out) * mask   (layers.py:143-146)
       mbar_wait(&acc_full[0], accph[0]); accph[0] ^= 1;
       fence_after_sync();
-      sum = 0.f;
-      for (int c = 0; c < 4; ++c) {
+      float sum = 0.f;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int c = grp + 2 * t;
         float eh[32];
         load_acc(EH, c);
 #pragma unroll
@@ -409,41 +492,47 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) eh[i] += v[i];
         load_acc(ACC0, c);
-        float b[32];
-        ld32(a.BOUT + c * 32, b);
+        const float* b = prm + kP_BOUT + c * 32;
 #pragma unroll
         for (int i = 0; i < 32; ++i) { v[i] = eh[i] + v[i] + b[i]; sum += v[i]; }
         store_tmem(ACC0 + c * 32, v);
       }
       tmem_st_wait();
-      const float mean3 = sum * (1.f / 128.f);
-      var = 0.f;
-      for (int c = 0; c < 4; ++c) {
-        load_acc(ACC0, c);
+      const float mean3 = row_total(sum, 2) * (1.f / 128.f);
+      float var = 0.f;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        load_acc(ACC0, grp + 2 * t);
 #pragma unroll
         for (int i = 0; i < 32; ++i) { float d = v[i] - mean3; var += d * d; }
       }
-      const float rstd3 = rsqrtf(var * (1.f / 128.f) + 1e-5f);
+      const float rstd3 = rsqrtf(row_total(var, 3) * (1.f / 128.f) + 1e-5f);
       float* orow = a.out + ((size_t)rr * K + (in_range ? k : 0)) * 128;
-      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int c = grp + 2 * t;
         load_acc(ACC0, c);
-        float gm[32], bt[32];
-        ld32(a.LN3G + c * 32, gm);
-        ld32(a.LN3B + c * 32, bt);
+        const float* gm = prm + kP_LN3G + c * 32;
+        const float* bt = prm + kP_LN3B + c * 32;
         if (in_range) {
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             float4 y;
-            int i = u * 4;
-            y.x = (matt != 0.f) ? (v[i + 0] - mean3) * rstd3 * gm[i + 0] + bt[i + 0] : 0.f;
-            y.y = (matt != 0.f) ? (v[i + 1] - mean3) * rstd3 * gm[i + 1] + bt[i + 1] : 0.f;
-            y.z = (matt != 0.f) ? (v[i + 2] - mean3) * rstd3 * gm[i + 2] + bt[i + 2] : 0.f;
-            y.w = (matt != 0.f) ? (v[i + 3] - mean3) * rstd3 * gm[i + 3] + bt[i + 3] : 0.f;
+            const int i = u * 4;
+            y.x = on ? (v[i + 0] - mean3) * rstd3 * gm[i + 0] + bt[i + 0] : 0.f;
+            y.y = on ? (v[i + 1] - mean3) * rstd3 * gm[i + 1] + bt[i + 1] : 0.f;
+            y.z = on ? (v[i + 2] - mean3) * rstd3 * gm[i + 2] + bt[i + 2] : 0.f;
+            y.w = on ? (v[i + 3] - mean3) * rstd3 * gm[i + 3] + bt[i + 3] : 0.f;
             *reinterpret_cast<float4*>(orow + c * 32 + i) = y;
           }
         }
       }
     }
+    // end of tile: both accumulators and the FFN operand have been fully read by this thread
+    fence_before_sync();
+    mbar_arrive(wk_done);
+    qbase += EDGE ? 30 : 10;
+    }  // tile loop
   }
 
   // ---- teardown: all tensor-core work of this CTA has been consumed by its workers; in a cluster nobody may exit
@@ -451,7 +540,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
   fence_before_sync();
   __syncthreads();
   if (CLUSTER > 1) cluster_sync_all();
-  if (warp == 4) tmem_dealloc<512>(tmem);
+  if (warp == 8) tmem_dealloc<512>(tmem);
 }
 
 template <bool EDGE, int PASSES, int CLUSTER>
@@ -464,9 +553,17 @@ static int launch(const Args& a, cudaStream_t stream) {
   }
   const long long R = (long long)a.S * a.G;
   unsigned tiles = (unsigned)((R + 3) / 4);
-  tiles = (tiles + CLUSTER - 1) / CLUSTER * CLUSTER;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  unsigned grid = tiles < (unsigned)num_sms ? tiles : (unsigned)num_sms;  // persistent: one CTA per SM
+  grid = grid / CLUSTER * CLUSTER;
+  if (grid == 0) grid = CLUSTER;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(tiles);
+  cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreadsTC);
   cfg.dynamicSmemBytes = kSmemTC;
   cfg.stream = stream;
