@@ -170,6 +170,79 @@ def workload_config(args):
             "parallelism": "one sweep per GPU, no data-path collective"}
 
 
+def _events_ms(fn, reps):
+    for _ in range(3):  # first call eager, second call captures the CUDA graph (small problems), third replays
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def run_secondary(model, dev, with_cpu):
+    """Second headline metric of BASELINE.json ("clash-grad ms @5k residues", configs[3]) and the single-complex
+    configurations (configs[0..2]) that are latency- rather than throughput-bound.  Device-timed, rank 0 only."""
+    import numpy as np
+
+    from packppi_b200 import compute_residue_clash, get_atom14_coords, proximal_optimizer, synthetic
+    from packppi_b200.batch import ComplexBatch, TENSOR_FIELDS
+    out = {}
+    # -- clash loss + analytic gradient and the full proximal loop on one 5000-residue complex
+    b = synthetic.make_complex((500,) * 10, seed=5000).to(dev)
+    b["X"] = (get_atom14_coords(b.X, b.residue_type, b.BB_D, b.SC_D) * b.atom_mask[..., None]).contiguous()
+    x = b.SC_D.clone().requires_grad_(True)
+
+    def fwd_bwd():
+        x.grad = None
+        compute_residue_clash(b, x).sum().backward()
+
+    out["clash_grad_ms_5k"] = _events_ms(fwd_bwd, 20)
+    out["clash_fwd_ms_5k"] = _events_ms(lambda: compute_residue_clash(b, b.SC_D), 20)
+    t0 = time.perf_counter()
+    snaps, losses = proximal_optimizer(b, b.SC_D, 12.0, 0.5, 1.0, 50)
+    torch.cuda.synchronize()
+    out["proximal_50_steps_ms_5k"] = 1e3 * (time.perf_counter() - t0)
+    out["proximal_loss_first_last_5k"] = [losses[0], losses[-1]]
+    out["peak_mem_GB"] = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    if with_cpu:
+        from oracle import prox_oracle as po
+        bc = b.to("cpu")
+        t0 = time.perf_counter()
+        po.clash_value_and_grad(bc, bc.SC_D, sparse=True)
+        out["cpu_port_clash_grad_ms_5k"] = 1e3 * (time.perf_counter() - t0)
+        out["cpu_note"] = ("sparse (KD-tree) CPU oracle; the reference's dense [N,N,14,14] formulation needs ~257 GB at "
+                           "5000 residues and cannot run")
+    # -- single complexes: 1BRS (195) and T1124 (739) from the golden inputs, synthetic 1500; one sample, 30 steps
+    gold = os.path.join(ROOT, "tests", "golden")
+    cases = []
+    for name in ("1brs", "t1124"):
+        with np.load(os.path.join(gold, name + ".npz")) as z:
+            cb = ComplexBatch(**{k: torch.from_numpy(z["in_" + k]) for k in TENSOR_FIELDS})
+        cb["num_proteins"], cb["max_size"] = 1, int(cb.X.shape[1])
+        cases.append((name, cb.to(dev)))
+    cases.append(("synthetic1500", synthetic.make_complex((500,) * 3, seed=1500).to(dev)))
+    for name, cb in cases:
+        L = int(cb.residue_mask.sum())
+
+        def run():
+            model._graph_cache = (None, model._graph_cache[1])  # rebuild graph + edge embedding, keep the buffers
+            return model.sampling(cb)
+
+        ms = _events_ms(run, 5)
+        out[f"sampling_{name}"] = {"residues": L, "ms": ms, "residue_steps_per_s": L * N_ODE / (ms * 1e-3)}
+    cb = cases[0][1]
+    chi = model.sampling(cb)
+    t0 = time.perf_counter()
+    proximal_optimizer(cb, chi, 12.0, 0.5, 1.0, 50)
+    torch.cuda.synchronize()
+    out["proximal_50_steps_ms_1brs"] = 1e3 * (time.perf_counter() - t0)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -179,6 +252,7 @@ def main():
     ap.add_argument("--impl", default="packppi_b200", choices=["packppi_b200", "reference"])
     ap.add_argument("--complexes", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the clash-grad @5k and single-complex timings")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -209,7 +283,7 @@ def main():
         outs = []
         for b in batches:
             bd = b.to(dev, non_blocking=True) if from_host else b
-            model._graph_cache = (None, None)  # a new complex every call: graph + edge embedding are part of the step
+            model._graph_cache = (None, model._graph_cache[1])  # new complex: graph + edge embedding are rebuilt every call
             chi = model.sampling(bd, n_samples=N_SAMPLES, generator=gen)
             outs.append(chi.to("cpu", non_blocking=False) if from_host else chi)
         return outs
@@ -285,6 +359,10 @@ def main():
     else:
         roof = None
 
+    secondary = None
+    if rank == 0 and not args.no_secondary:
+        secondary = run_secondary(model, dev, not args.no_cpu_baseline)
+
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         small = min(micro_host[0:1], key=lambda b: b.max_size)
@@ -307,7 +385,7 @@ def main():
                 "config": workload_config(args), "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": "residue.steps/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / e2e_steps},
-                "gpu_launches": launches, "residues_per_gpu": residues}
+                "gpu_launches": launches, "residues_per_gpu": residues, "secondary": secondary}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -2,6 +2,7 @@
 memory and streams only; every arithmetic step of the hot path is a kernel of libpackppi_b200.so.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -11,6 +12,9 @@ from .weights import pack_tc_stream, pack_weights
 
 SIGMA_MIN, SIGMA_MAX = 0.01 * np.pi, np.pi  # schedule.py:148-149 defaults
 TOP_K = 32
+# Below this many residue rows (S*G) a denoising step is launch-latency bound (17 launches, ~0.1 ms of device work),
+# so repeated sampling on buffers of the same shape replays one captured CUDA graph of the whole 30-step loop.
+GRAPH_ROWS_MAX = int(os.environ.get("PACKPPI_B200_GRAPH_ROWS", "16384"))
 
 
 def _f32(t, dev):
@@ -57,8 +61,10 @@ class Graph:
         self.B, self.L = int(X.shape[0]), int(X.shape[1])
         self.G = self.B * self.L
         self.K = min(top_k, self.L)
-        self.X = _f32(X, dev)
-        self.mask = _f32(residue_mask, dev)
+        self.X = _f32(X, dev).clone()
+        self.mask = _f32(residue_mask, dev).clone()
+        self._replay = {}  # captured CUDA graphs of the sampling loop, keyed by (S, steps, ...)
+        self._seen = set()
         G, K = self.G, self.K
         self.E_idx = torch.empty(self.B, self.L, K, dtype=torch.int64, device=dev)
         self.nbr = torch.empty(G, K, dtype=torch.int32, device=dev)
@@ -66,14 +72,24 @@ class Graph:
         self.mask_attend = torch.empty(G, K, dtype=torch.float32, device=dev)
         self.msum = torch.empty(G, dtype=torch.float32, device=dev)
         self.geo = torch.empty(G, _lib.load().pp_geo_stride(), dtype=torch.float32, device=dev)
-        _lib.call("pp_knn_build", self.X, self.mask, self.B, self.L, K, self.E_idx, self.nbr, self.D_neighbors,
-                  self.mask_attend, self.msum)
-        _lib.call("pp_geometry_build", self.X, G, self.geo)
         self.hE0 = None
+        self._build()
+
+    def _build(self):
+        _lib.call("pp_knn_build", self.X, self.mask, self.B, self.L, self.K, self.E_idx, self.nbr, self.D_neighbors,
+                  self.mask_attend, self.msum)
+        _lib.call("pp_geometry_build", self.X, self.G, self.geo)
+
+    def rebuild(self, X, residue_mask):
+        """Same shape, new complex: refill the existing buffers in place (pointers stay valid for captured graphs)."""
+        self.X.copy_(X)
+        self.mask.copy_(residue_mask)
+        self._build()
 
     def edge_embed(self, wblob, residue_index, chain_indices):
         dev = self.X.device
-        self.hE0 = torch.empty(self.G, self.K, 128, dtype=torch.float32, device=dev)
+        if self.hE0 is None:
+            self.hE0 = torch.empty(self.G, self.K, 128, dtype=torch.float32, device=dev)
         _lib.call("pp_edge_embed", wblob, self.geo, self.nbr, _i64(residue_index, dev), _i64(chain_indices, dev),
                   self.G, self.K, self.hE0)
         return self.hE0
@@ -117,8 +133,15 @@ class Engine:
         self._ws = {}
 
     # ------------------------------------------------------------------ graph
-    def build_graph(self, batch, with_edges=True):
-        g = Graph(batch.X.to(self.dev), batch.residue_mask.to(self.dev))
+    def build_graph(self, batch, with_edges=True, reuse=None):
+        """kNN graph, geometry records and edge embedding of `batch`.  `reuse`: a Graph of the same shape whose
+        buffers (and captured CUDA graphs) are refilled in place instead of allocating new ones."""
+        X, mask = batch.X.to(self.dev), batch.residue_mask.to(self.dev)
+        if reuse is not None and (reuse.B, reuse.L) == tuple(X.shape[:2]) and reuse.X.device == X.device:
+            g = reuse
+            g.rebuild(X, mask)
+        else:
+            g = Graph(X, mask)
         if with_edges:
             g.edge_embed(self.wblob, batch.residue_index, batch.chain_indices)
         return g
@@ -202,27 +225,51 @@ class Engine:
             out.append((float(time), float(c), float(w)))
         return out
 
-    def sample(self, graph, batch, chi_init, n_steps=30, annealed_temp=3.0, trajectory=None):
-        """Reverse-ODE loop (TorsionalDiffusion.py:259-280) on S samples that share `graph`.
-
-        chi_init [S*G,4] on the device; returns the final chi [S*G,4] (a new tensor)."""
-        G, K = graph.G, graph.K
-        S = chi_init.shape[0] // G
-        ws = self.workspace(G, K, S)
-        ni = self.node_inputs(batch)
-        step_mask = (batch.chi_1pi_periodic_mask.to(self.dev).reshape(-1, 4).bool() |
-                     batch.chi_2pi_periodic_mask.to(self.dev).reshape(-1, 4).bool()).to(torch.uint8).contiguous()
-        chi = chi_init.clone().contiguous()
-        tbuf = torch.empty(1, dtype=torch.float32, device=self.dev)
-        coefs = self.ode_coefficients(n_steps, annealed_temp)
-        tvals = torch.tensor([c[0] for c in coefs], dtype=torch.float32, device=self.dev)
+    def _run_steps(self, graph, ws, ni, step_mask, chi, tvals, coefs, trajectory=None):
+        G, S = graph.G, ws.S
         for j, (_, c, w) in enumerate(coefs):
-            tbuf = tvals[j:j + 1]
-            self.forward_layers(graph, ws, ni, chi, tbuf, 0)
+            self.forward_layers(graph, ws, ni, chi, tvals[j:j + 1], 0)
             _lib.call("pp_decode_step", self.wblob, ws.hV, G, S, None, 1, c, w, step_mask, ni["chi_mask"], chi)
             if trajectory is not None:
                 trajectory.append(chi.clone())
-        return chi
+
+    def sample(self, graph, batch, chi_init, n_steps=30, annealed_temp=3.0, trajectory=None):
+        """Reverse-ODE loop (TorsionalDiffusion.py:259-280) on S samples that share `graph`.
+
+        chi_init [S*G,4] on the device; returns the final chi [S*G,4] (a new tensor).  Small problems that come back
+        with the same buffers (decoy loops on one complex, same-shape batches through `build_graph(reuse=)`) replay a
+        captured CUDA graph of the whole loop from the second call on."""
+        G, K = graph.G, graph.K
+        S = chi_init.shape[0] // G
+        ni = self.node_inputs(batch)
+        step_mask = (batch.chi_1pi_periodic_mask.to(self.dev).reshape(-1, 4).bool() |
+                     batch.chi_2pi_periodic_mask.to(self.dev).reshape(-1, 4).bool()).to(torch.uint8).contiguous()
+        coefs = self.ode_coefficients(n_steps, annealed_temp)
+        key = (S, n_steps, float(annealed_temp), self.mode, self.cluster, id(self))
+        small = S * G <= GRAPH_ROWS_MAX and trajectory is None and _lib.PROFILE is None and GRAPH_ROWS_MAX > 0
+        if not small or (key not in graph._seen and key not in graph._replay):
+            graph._seen.add(key)
+            chi = chi_init.clone().contiguous()
+            tvals = torch.tensor([c[0] for c in coefs], dtype=torch.float32, device=self.dev)
+            self._run_steps(graph, self.workspace(G, K, S), ni, step_mask, chi, tvals, coefs, trajectory)
+            return chi
+        st = graph._replay.get(key)
+        if st is None:  # second call with these buffers: capture
+            st = dict(ws=Workspace(G, K, S, self.dev), chi=chi_init.clone().contiguous(),
+                      ni={k: v.clone() for k, v in ni.items()}, step_mask=step_mask.clone(),
+                      tvals=torch.tensor([c[0] for c in coefs], dtype=torch.float32, device=self.dev))
+            torch.cuda.synchronize(self.dev)
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg):
+                self._run_steps(graph, st["ws"], st["ni"], st["step_mask"], st["chi"], st["tvals"], coefs)
+            st["graph"] = cg
+            graph._replay[key] = st
+        st["chi"].copy_(chi_init)
+        for k, v in ni.items():
+            st["ni"][k].copy_(v)
+        st["step_mask"].copy_(step_mask)
+        st["graph"].replay()
+        return st["chi"].clone()
 
     # ------------------------------------------------------------------ atom14 / clash / proximal
     def atom14(self, X, residue_type, chi):
@@ -260,6 +307,7 @@ class ClashContext:
         self.list = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
         _lib.call("pp_clash_neighbours", *args, 1, self.reach, None, self.start, self.list)
         self._ws = {}
+        self._prox = {}
 
     def scratch(self, S):
         if S not in self._ws:
@@ -279,28 +327,45 @@ class ClashContext:
                   per_res, grad, ws["atoms4"], ws["axes"], ws["bound"])
         return per_res, grad
 
-    def proximal(self, sc_d, lamda, num_steps, lr=1e-2, beta1=0.9, beta2=0.999, eps=1e-8):
-        """optimize.py:21-73 for one complex.  Returns (snapshots [num_steps,G,4], losses [num_steps], mask [G,4]);
-        everything stays on the device, the caller decides when to synchronise."""
-        assert self.B == 1
-        G, dev = self.G, self.dev
+    def _prox_run(self, st, lamda, num_steps, lr, beta1, beta2, eps):
+        G = self.G
         ws = self.scratch(1)
-        f = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)  # noqa: E731
-        mask = torch.zeros(G, 4, dtype=torch.uint8, device=dev)
-        z, x, m, v = f(G, 4), f(G, 4), f(G, 4), f(G, 4)
-        per_res, mean = f(G), f(2)
-        partial = f(int(_lib.load().pp_prox_partial_floats(G)))
-        snaps = f(num_steps, G, 4)
-        losses = f(num_steps, 2)
-        sc_d = sc_d.contiguous()
-        static = (self.tables.geo, self.lower, self.upper, self.X, self.rtype, self.exists, self.start, self.list, sc_d)
-        _lib.call("pp_prox_init", *static, G, self.tol, self.max_cut, mask, z, x, m, v, per_res, mean, ws["atoms4"],
-                  ws["axes"], ws["bound"], partial)
+        static = (self.tables.geo, self.lower, self.upper, self.X, self.rtype, self.exists, self.start, self.list,
+                  st["sc_d"])
+        _lib.call("pp_prox_init", *static, G, self.tol, self.max_cut, st["mask"], st["z"], st["x"], st["m"], st["v"],
+                  st["per_res"], st["mean"], ws["atoms4"], ws["axes"], ws["bound"], st["partial"])
         for k in range(num_steps):
             t = k + 1
             step_size = lr / (1 - beta1 ** t)  # torch.optim.Adam, single-tensor path
             bc2_sqrt = math.sqrt(1 - beta2 ** t)
-            _lib.call("pp_prox_step", *static, mask, z, x, m, v, G, self.tol, self.max_cut, float(lamda), step_size,
-                      bc2_sqrt, beta1, beta2, eps, snaps[k], losses[k], per_res, ws["atoms4"], ws["axes"], ws["bound"],
-                      partial)
-        return snaps, losses[:, 0], mask
+            _lib.call("pp_prox_step", *static, st["mask"], st["z"], st["x"], st["m"], st["v"], G, self.tol,
+                      self.max_cut, float(lamda), step_size, bc2_sqrt, beta1, beta2, eps, st["snaps"][k],
+                      st["losses"][k], st["per_res"], ws["atoms4"], ws["axes"], ws["bound"], st["partial"])
+
+    def proximal(self, sc_d, lamda, num_steps, lr=1e-2, beta1=0.9, beta2=0.999, eps=1e-8):
+        """optimize.py:21-73 for one complex.  Returns (snapshots [num_steps,G,4], losses [num_steps], mask [G,4]);
+        everything stays on the device, the caller decides when to synchronise.  The 1 + 3*num_steps launches are
+        captured in a CUDA graph the second time the same context runs the same schedule."""
+        assert self.B == 1
+        G, dev = self.G, self.dev
+        key = (int(num_steps), float(lamda), lr, beta1, beta2, eps)
+        st = self._prox.get(key)
+        if st is None:
+            f = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)  # noqa: E731
+            st = dict(sc_d=f(G, 4), mask=torch.zeros(G, 4, dtype=torch.uint8, device=dev), z=f(G, 4), x=f(G, 4),
+                      m=f(G, 4), v=f(G, 4), per_res=f(G), mean=f(2), snaps=f(num_steps, G, 4), losses=f(num_steps, 2),
+                      partial=f(int(_lib.load().pp_prox_partial_floats(G))), calls=0, graph=None)
+            self._prox = {key: st}  # one schedule at a time keeps the memory bounded
+        st["sc_d"].copy_(sc_d.reshape(G, 4))
+        st["calls"] += 1
+        if st["calls"] == 1 or GRAPH_ROWS_MAX <= 0:
+            self._prox_run(st, lamda, num_steps, lr, beta1, beta2, eps)
+        else:
+            if st["graph"] is None:
+                torch.cuda.synchronize(dev)
+                cg = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(cg):
+                    self._prox_run(st, lamda, num_steps, lr, beta1, beta2, eps)
+                st["graph"] = cg
+            st["graph"].replay()
+        return st["snaps"].clone(), st["losses"][:, 0].clone(), st["mask"].clone()

@@ -236,7 +236,11 @@ class TDiffusionModule(_PackedModule):
         eng = self.engine(batch.X.device)
         key = (id(batch), batch.X.data_ptr(), getattr(self, "_engine_sig", None))
         if self._graph_cache[0] != key:
-            self._graph_cache = (key, eng.build_graph(batch))
+            prev = self._graph_cache[1]
+            if prev is not None and (prev.B, prev.L) != tuple(batch.X.shape[:2]):
+                prev = None
+                self._graph_cache = (None, None)  # release the old buffers before the new ones are allocated
+            self._graph_cache = (key, eng.build_graph(batch, reuse=prev))
         return eng, self._graph_cache[1]
 
     # -- reference API ----------------------------------------------------------------------------------
