@@ -97,6 +97,10 @@ int pp_ipmp_edge_tc(const float* weights, int64_t layer, int64_t path, const flo
                     const float* hE_in, int64_t he_shared, const float* wsA, const float* wsN, const float* wsP,
                     float* out, int64_t passes, int64_t cluster, pp_stream_t stream);
 
+/* Diagnostics: later pp_ipmp_edge_tc launches write clock64() stamps of the phase boundaries of their first tile
+ * (CTA 0, one worker thread) into trace (device memory, >= 32 uint64); NULL switches it off. */
+int pp_set_tc_trace(uint64_t* trace);
+
 /* decoder_score (models/TorsionalDiffusion.py:62-68,106-108) and, if do_step, both SO2VESchedule.step calls in ode
  * mode plus wrap and mask (models/components/schedule.py:198-235, TorsionalDiffusion.py:272-280):
  *   chi <- wrap(chi + [step_mask] c_ode (score * w_anneal)) * chi_mask.

@@ -30,8 +30,8 @@ using namespace umma;
 
 constexpr int kRows = 128;
 constexpr int kKC = 32;
-constexpr int kSA = 2;   // A ring: slots of 32 k-columns (hi + lo images, 32 KB)
-constexpr int kSB = 8;   // B ring: sub-slots of 16 k-columns (hi + lo images, 16 KB): deep, to cover the L2 latency
+constexpr int kSA = 3;   // A ring: slots of 32 k-columns (hi + lo images, 32 KB)
+constexpr int kSB = 6;   // B ring: sub-slots of 16 k-columns (hi + lo images, 16 KB)
 constexpr int kImgFloats = kRows * kKC;          // one operand image (hi or lo) of a 32-column chunk
 constexpr uint32_t kImgBytes = kImgFloats * 4;   // 16 KB
 constexpr int kSlotFloats = 2 * kImgFloats;      // hi + lo
@@ -62,6 +62,7 @@ struct Args {
   const float* hE_in; int he_shared;
   const float *A, *Nn, *pglob;
   float* out;             // node path: accsum [R][128]; edge path: hE_out [R][K][128]
+  unsigned long long* trace;  // optional: clock64 stamps of CTA 0 / first tile (pp_set_tc_trace), else null
 };
 
 struct Ring {
@@ -237,12 +238,21 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
           // G3 -> ACC0
           for (int c = 0; c < 4; ++c) chunk(true, ACC0, 0, kKC, c == 0);
           mma_commit(&acc_full[0]);
+          // FFN, software-pipelined by one slice: while the workers turn slice j into the A operand of FFN-out j,
+          // the tensor pipe runs FFN-out j-1 and FFN-in j+1.  A whole hidden slice (4 chunks) is parked in the A ring.
+          mbar_wait(wk_done, wk_phase);  // e is in TMEM, ACC0 / ACC1 are drained
+          wk_phase ^= 1;
+          fence_after_sync();
+          for (int c = 0; c < 4; ++c) chunk(false, ACC1, c * kKC, kKC, c == 0);  // FFN-in slice 0: A = e from TMEM
+          mma_commit(&acc_full[1]);
           for (int j = 0; j < 4; ++j) {
-            mbar_wait(wk_done, wk_phase);  // e is in TMEM (j = 0) / ACC1 has been drained (j > 0)
-            wk_phase ^= 1;
-            fence_after_sync();
-            for (int c = 0; c < 4; ++c) chunk(false, ACC1, c * kKC, kKC, c == 0);  // FFN-in slice j: A = e from TMEM
-            mma_commit(&acc_full[1]);
+            if (j + 1 < 4) {
+              mbar_wait(wk_done, wk_phase);  // slice j has been read out of ACC1 (and published)
+              wk_phase ^= 1;
+              fence_after_sync();
+              for (int c = 0; c < 4; ++c) chunk(false, ACC1, c * kKC, kKC, c == 0);  // FFN-in slice j+1
+              mma_commit(&acc_full[1]);
+            }
             for (int c = 0; c < 4; ++c) chunk(true, ACC0, 0, kKC, j == 0 && c == 0);  // FFN-out slice j accumulates
           }
           mma_commit(&acc_full[0]);
@@ -261,39 +271,31 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t accph[2] = {0, 0};
     int qbase = 0;  // running A-chunk counter (ring position persists across tiles)
-    for (int it = 0; it < niter; ++it) {
-    const int rb = (it * (int)gridDim.x + (int)blockIdx.x) * 4;
-    const int r = rb + rl;
-    const bool in_range = r < R && k < K;
-    const int rr = min(r, R - 1);
-    const int s = rr / a.G, g = rr - s * a.G;
-    const float matt = in_range ? a.matt[(size_t)g * K + k] : 0.f;
-    const bool on = matt != 0.f;
-    const int jrow = in_range ? s * a.G + a.nbr[(size_t)g * K + k] : rr;
-    const float* hrow = a.hE_in + ((size_t)(a.he_shared ? g : rr) * K + (in_range ? k : 0)) * 128;
-    float v[32];
 
-    // A chunk number q of the tile's fixed schedule -> ring slot q % kSA, (q / kSA)-th use of that slot
-    auto publish = [&](int qrel, const float* vals, int kc) {
-      const int q = qbase + qrel;
-      const int slot = q % kSA;
-      mbar_wait(&a_empty[slot], ((q / kSA) & 1) ^ 1);
-      put_chunk<PASSES>(Aring + slot * kSlotFloats, m, vals, kc);
-      fence_async_smem();
-      mbar_arrive(&a_full[slot]);
+    struct RowCtx {  // where this thread's edge row of a tile lives
+      int r, rr, g, jrow;
+      bool in_range, on;
+      const float* hrow;
     };
-    auto load_acc = [&](uint32_t acc, int c) {
-      uint32_t u[32];
-      tmem_ld32(acc + lane_base + c * 32, u);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(u[i]);
+    auto row_ctx = [&](int it) {
+      RowCtx c;
+      c.r = (it * (int)gridDim.x + (int)blockIdx.x) * 4 + rl;
+      c.in_range = c.r < R && k < K;
+      c.rr = min(c.r, R - 1);
+      const int s = c.rr / a.G;
+      c.g = c.rr - s * a.G;
+      c.on = c.in_range && a.matt[(size_t)c.g * K + k] != 0.f;
+      c.jrow = c.in_range ? s * a.G + a.nbr[(size_t)c.g * K + k] : c.rr;
+      c.hrow = a.hE_in + ((size_t)(a.he_shared ? c.g : c.rr) * K + (c.in_range ? k : 0)) * 128;
+      return c;
     };
-    auto store_tmem = [&](uint32_t col, const float* vals) {
-      uint32_t u[32];
+    auto load_h = [&](const RowCtx& c, float4 (&h)[2][8]) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) u[i] = __float_as_uint(vals[i]);
-      tmem_st32(col + lane_base, u);
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          h[t][u] = c.in_range ? *reinterpret_cast<const float4*>(c.hrow + (grp + 2 * t) * 32 + u * 4)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     auto row_total = [&](float partial, int which) -> float {  // sum over the two threads that share a row
       red[(which * 2 + grp) * 128 + m] = partial;
@@ -301,237 +303,298 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
       return red[(which * 2) * 128 + m] + red[(which * 2 + 1) * 128 + m];
     };
 
-    // ---- first A operand: h_E row (chunks 0-3) and the pair geometry (chunk 4: 32 columns, chunk 5: 8 columns)
-    {
-      float4 h[2][8];
-#pragma unroll
-      for (int t = 0; t < 2; ++t)
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-          h[t][u] = in_range ? *reinterpret_cast<const float4*>(hrow + (grp + 2 * t) * 32 + u * 4)
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float* fr = a.geo + (size_t)g * PP_GEO_STRIDE;
-      const float* pi = a.pglob + (size_t)rr * 24;
-      const float* pj = a.pglob + (size_t)jrow * 24;
-      float geo[32];
-#pragma unroll
-      for (int pt = 0; pt < 8; ++pt) {
-        float jx = pj[pt * 3], jy = pj[pt * 3 + 1], jz = pj[pt * 3 + 2];
-        if (grp == 0) {  // neighbour points in the local frame and their norms   (layers.py:93-97)
-          float dx = jx - fr[9], dy = jy - fr[10], dz = jz - fr[11];
-          float qx = fr[0] * dx + fr[3] * dy + fr[6] * dz;
-          float qy = fr[1] * dx + fr[4] * dy + fr[7] * dz;
-          float qz = fr[2] * dx + fr[5] * dy + fr[8] * dz;
-          geo[pt * 3] = qx; geo[pt * 3 + 1] = qy; geo[pt * 3 + 2] = qz;
-          geo[24 + pt] = sqrtf(qx * qx + qy * qy + qz * qz + 1e-8f);
-        } else {         // distances between the global points   (layers.py:99-103)
-          float gx = pi[pt * 3] - jx, gy = pi[pt * 3 + 1] - jy, gz = pi[pt * 3 + 2] - jz;
-          geo[pt] = sqrtf(gx * gx + gy * gy + gz * gz + 1e-8f);
-        }
+    auto prefetch_h = [&](const RowCtx& c) {  // pull the next tile's h_E lines into L2 (no registers held)
+      if (c.in_range) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(c.hrow + grp * 32));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(c.hrow + (grp + 2) * 32));
       }
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { v[u * 4] = h[t][u].x; v[u * 4 + 1] = h[t][u].y; v[u * 4 + 2] = h[t][u].z; v[u * 4 + 3] = h[t][u].w; }
-        publish(grp + 2 * t, v, kKC);
-      }
-      if (grp == 0) publish(4, geo, kKC); else publish(5, geo, 8);
-    }
+    };
 
-    // ---- epilogue of G1: x1 = relu(acc + A_i + N_j); the two gathered rows are fetched before the wait
-    {
-      const float* Ai = a.A + (size_t)rr * 128;
-      const float* Nj = a.Nn + (size_t)jrow * 128;
-      float4 an[2][8];
+    RowCtx cx = row_ctx(0);
+    float4 hpre[2][8];  // h_E columns of this thread for the tile about to start
+    if (!EDGE) load_h(cx, hpre);
+
+    for (int it = 0; it < niter; ++it) {
+      if (EDGE) load_h(cx, hpre);
+      const bool on = cx.on, in_range = cx.in_range;
+      const int r = cx.r, rr = cx.rr;
+      float v[32];
+      int stamp_i = 0;
+      auto stamp = [&]() {
+        if (a.trace && blockIdx.x == 0 && it == 0 && tid == 0) a.trace[stamp_i] = clock64();
+        ++stamp_i;
+      };
+      stamp();  // 0: tile start
+      // A chunk number q of the tile's fixed schedule -> ring slot q % kSA, (q / kSA)-th use of that slot
+      auto publish = [&](int qrel, const float* vals, int kc) {
+        const int q = qbase + qrel;
+        const int slot = q % kSA;
+        mbar_wait(&a_empty[slot], ((q / kSA) & 1) ^ 1);
+        put_chunk<PASSES>(Aring + slot * kSlotFloats, m, vals, kc);
+        fence_async_smem();
+        mbar_arrive(&a_full[slot]);
+      };
+      auto load_acc = [&](uint32_t acc, int c, float (&dst)[32]) {
+        uint32_t u[32];
+        tmem_ld32(acc + lane_base + c * 32, u);
+        tmem_ld_wait();
 #pragma unroll
-      for (int t = 0; t < 2; ++t)
+        for (int i = 0; i < 32; ++i) dst[i] = __uint_as_float(u[i]);
+      };
+      auto store_tmem = [&](uint32_t col, const float* vals) {
+        uint32_t u[32];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          float4 x = *reinterpret_cast<const float4*>(Ai + (grp + 2 * t) * 32 + u * 4);
-          float4 y = *reinterpret_cast<const float4*>(Nj + (grp + 2 * t) * 32 + u * 4);
-          an[t][u] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+        for (int i = 0; i < 32; ++i) u[i] = __float_as_uint(vals[i]);
+        tmem_st32(col + lane_base, u);
+      };
+
+      // ---- first A operand: h_E row (chunks 0-3) and the pair geometry (chunk 4: 32 columns, chunk 5: 8 columns)
+      {
+        const float4* fr4 = reinterpret_cast<const float4*>(a.geo + (size_t)cx.g * PP_GEO_STRIDE);
+        const float4* pi4 = reinterpret_cast<const float4*>(a.pglob + (size_t)rr * 24);
+        const float4* pj4 = reinterpret_cast<const float4*>(a.pglob + (size_t)cx.jrow * 24);
+        float fr[12], pi[24], pj[24];
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+          float4 x = pj4[u];
+          pj[u * 4] = x.x; pj[u * 4 + 1] = x.y; pj[u * 4 + 2] = x.z; pj[u * 4 + 3] = x.w;
         }
-      mbar_wait(&acc_full[0], accph[0]); accph[0] ^= 1;
-      fence_after_sync();
+        if (grp == 0) {
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        load_acc(ACC0, grp + 2 * t);
+          for (int u = 0; u < 3; ++u) {
+            float4 x = fr4[u];
+            fr[u * 4] = x.x; fr[u * 4 + 1] = x.y; fr[u * 4 + 2] = x.z; fr[u * 4 + 3] = x.w;
+          }
+        } else {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          v[u * 4 + 0] = fmaxf(v[u * 4 + 0] + an[t][u].x, 0.f);
-          v[u * 4 + 1] = fmaxf(v[u * 4 + 1] + an[t][u].y, 0.f);
-          v[u * 4 + 2] = fmaxf(v[u * 4 + 2] + an[t][u].z, 0.f);
-          v[u * 4 + 3] = fmaxf(v[u * 4 + 3] + an[t][u].w, 0.f);
-        }
-        publish(6 + grp + 2 * t, v, kKC);
-      }
-    }
-    // ---- epilogue of G2: x2 = relu(acc + b2)
-    mbar_wait(&acc_full[1], accph[1]); accph[1] ^= 1;
-    fence_after_sync();
-    if (!EDGE) {
-      // node path: masked sum over the 32 edges of the residue (= the 32 lanes of this warp), layers.py:125-127
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int c = grp + 2 * t;
-        load_acc(ACC1, c);
-        const float* b = prm + kP_B2 + c * 32;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = on ? fmaxf(v[i] + b[i], 0.f) : 0.f;
-        // transpose-reduce: after the 5 steps lane l holds the sum of column l over the 32 lanes
-#pragma unroll
-        for (int step = 16; step >= 1; step >>= 1) {
-          const bool upper = (lane & step) != 0;
-#pragma unroll
-          for (int i = 0; i < step; ++i) {
-            float keep = upper ? v[i + step] : v[i];
-            float send = upper ? v[i] : v[i + step];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+          for (int u = 0; u < 6; ++u) {
+            float4 x = pi4[u];
+            pi[u * 4] = x.x; pi[u * 4 + 1] = x.y; pi[u * 4 + 2] = x.z; pi[u * 4 + 3] = x.w;
           }
         }
-        if (r < R) a.out[(size_t)r * 128 + c * 32 + lane] = v[0];
-      }
-    } else {
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int c = grp + 2 * t;
-        load_acc(ACC1, c);
-        const float* b = prm + kP_B2 + c * 32;
+        for (int t = 0; t < 2; ++t) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + b[i], 0.f);
-        publish(10 + c, v, kKC);
+          for (int u = 0; u < 8; ++u) {
+            v[u * 4] = hpre[t][u].x; v[u * 4 + 1] = hpre[t][u].y; v[u * 4 + 2] = hpre[t][u].z; v[u * 4 + 3] = hpre[t][u].w;
+          }
+          publish(grp + 2 * t, v, kKC);
+        }
+        float geo[32];
+#pragma unroll
+        for (int pt = 0; pt < 8; ++pt) {
+          const float jx = pj[pt * 3], jy = pj[pt * 3 + 1], jz = pj[pt * 3 + 2];
+          if (grp == 0) {  // neighbour points in the local frame and their norms   (layers.py:93-97)
+            float dx = jx - fr[9], dy = jy - fr[10], dz = jz - fr[11];
+            float qx = fr[0] * dx + fr[3] * dy + fr[6] * dz;
+            float qy = fr[1] * dx + fr[4] * dy + fr[7] * dz;
+            float qz = fr[2] * dx + fr[5] * dy + fr[8] * dz;
+            geo[pt * 3] = qx; geo[pt * 3 + 1] = qy; geo[pt * 3 + 2] = qz;
+            geo[24 + pt] = sqrtf(qx * qx + qy * qy + qz * qz + 1e-8f);
+          } else {         // distances between the global points   (layers.py:99-103)
+            float gx = pi[pt * 3] - jx, gy = pi[pt * 3 + 1] - jy, gz = pi[pt * 3 + 2] - jz;
+            geo[pt] = sqrtf(gx * gx + gy * gy + gz * gz + 1e-8f);
+          }
+        }
+        if (grp == 0) publish(4, geo, kKC); else publish(5, geo, 8);
       }
-      // ---- epilogue of G3: e = LN2(h_E + mask * (acc + b3))   (layers.py:139-142); e -> TMEM as (hi, lo)
+      stamp();  // 1: first operand published
+
+      // ---- epilogue of G1: x1 = relu(acc + A_i + N_j); the two gathered rows are fetched before the wait
       {
-        float4 h[2][8];
+        const float* Ai = a.A + (size_t)rr * 128;
+        const float* Nj = a.Nn + (size_t)cx.jrow * 128;
+        float4 an[2][8];
 #pragma unroll
         for (int t = 0; t < 2; ++t)
 #pragma unroll
-          for (int u = 0; u < 8; ++u)
-            h[t][u] = in_range ? *reinterpret_cast<const float4*>(hrow + (grp + 2 * t) * 32 + u * 4)
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int u = 0; u < 8; ++u) {
+            float4 x = *reinterpret_cast<const float4*>(Ai + (grp + 2 * t) * 32 + u * 4);
+            float4 y = *reinterpret_cast<const float4*>(Nj + (grp + 2 * t) * 32 + u * 4);
+            an[t][u] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+          }
         mbar_wait(&acc_full[0], accph[0]); accph[0] ^= 1;
         fence_after_sync();
+        stamp();  // 2: G1 complete
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          load_acc(ACC0, grp + 2 * t, v);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            v[u * 4 + 0] = fmaxf(v[u * 4 + 0] + an[t][u].x, 0.f);
+            v[u * 4 + 1] = fmaxf(v[u * 4 + 1] + an[t][u].y, 0.f);
+            v[u * 4 + 2] = fmaxf(v[u * 4 + 2] + an[t][u].z, 0.f);
+            v[u * 4 + 3] = fmaxf(v[u * 4 + 3] + an[t][u].w, 0.f);
+          }
+          publish(6 + grp + 2 * t, v, kKC);
+        }
+      }
+      stamp();  // 3: x1 published
+      // next tile's row: resolve it and (node path) start fetching its h_E columns now
+      RowCtx nx = cx;
+      if (it + 1 < niter) nx = row_ctx(it + 1);
+      if (!EDGE && it + 1 < niter) load_h(nx, hpre);
+
+      // ---- epilogue of G2: x2 = relu(acc + b2)
+      mbar_wait(&acc_full[1], accph[1]); accph[1] ^= 1;
+      fence_after_sync();
+      stamp();  // 4: G2 complete
+      if (!EDGE) {
+        // node path: masked sum over the 32 edges of the residue (= the 32 lanes of this warp), layers.py:125-127
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int c = grp + 2 * t;
+          load_acc(ACC1, c, v);
+          const float* b = prm + kP_B2 + c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = on ? fmaxf(v[i] + b[i], 0.f) : 0.f;
+          // transpose-reduce: after the 5 steps lane l holds the sum of column l over the 32 lanes
+#pragma unroll
+          for (int step = 16; step >= 1; step >>= 1) {
+            const bool upper = (lane & step) != 0;
+#pragma unroll
+            for (int i = 0; i < step; ++i) {
+              float keep = upper ? v[i + step] : v[i];
+              float send = upper ? v[i] : v[i + step];
+              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+            }
+          }
+          if (r < R) a.out[(size_t)r * 128 + c * 32 + lane] = v[0];
+        }
+      } else {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int c = grp + 2 * t;
+          load_acc(ACC1, c, v);
+          const float* b = prm + kP_B2 + c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + b[i], 0.f);
+          publish(10 + c, v, kKC);
+        }
+        stamp();  // 5: x2 published
+        // ---- epilogue of G3: e = LN2(h_E + mask * (acc + b3))   (layers.py:139-142); e -> TMEM as (hi, lo)
+        {
+          float4 h[2][8];
+          load_h(cx, h);  // residual; second read of the tile's own rows, L2 resident
+          mbar_wait(&acc_full[0], accph[0]); accph[0] ^= 1;
+          fence_after_sync();
+          stamp();  // 6: G3 complete
+          float x[2][32];
+          float sum = 0.f;
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int c = grp + 2 * t;
+            load_acc(ACC0, c, v);
+            const float* b = prm + kP_B3 + c * 32;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float hh[4] = {h[t][u].x, h[t][u].y, h[t][u].z, h[t][u].w};
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                const int i = u * 4 + q4;
+                x[t][i] = hh[q4] + (on ? v[i] + b[i] : 0.f);
+                sum += x[t][i];
+              }
+            }
+          }
+          const float mean = row_total(sum, 0) * (1.f / 128.f);
+          float var = 0.f;
+#pragma unroll
+          for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { float d = x[t][i] - mean; var += d * d; }
+          const float rstd = rsqrtf(row_total(var, 1) * (1.f / 128.f) + 1e-5f);
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int c = grp + 2 * t;
+            const float* gm = prm + kP_LN2G + c * 32;
+            const float* bt = prm + kP_LN2B + c * 32;
+            float lo[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float e = (x[t][i] - mean) * rstd * gm[i] + bt[i];
+              split_tf32(e, v[i], lo[i]);
+            }
+            store_tmem(EH + c * 32, v);
+            store_tmem(EL + c * 32, lo);
+          }
+          tmem_st_wait();
+          fence_before_sync();
+          mbar_arrive(wk_done);
+          stamp();  // 7: e in TMEM
+        }
+        if (it + 1 < niter) prefetch_h(nx);
+        // ---- FFN: hidden slice j = relu(acc + b_in[j]) -> the four A chunks of FFN-out slice j
+        for (int j = 0; j < 4; ++j) {
+          mbar_wait(&acc_full[1], accph[1]); accph[1] ^= 1;
+          fence_after_sync();
+          stamp();  // 8 + 2j: FFN-in slice j complete
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int c = grp + 2 * t;
+            load_acc(ACC1, c, v);
+            if (t == 1 && j < 3) {  // ACC1 is drained for this thread: the next FFN-in slice may overwrite it
+              fence_before_sync();
+              mbar_arrive(wk_done);
+            }
+            const float* b = prm + kP_BIN + j * 128 + c * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + b[i], 0.f);
+            publish(14 + 4 * j + c, v, kKC);
+          }
+          stamp();  // 9 + 2j: hidden slice j published
+        }
+        // ---- final: y = LN3(e + acc + b_out) * mask   (layers.py:143-146)
+        mbar_wait(&acc_full[0], accph[0]); accph[0] ^= 1;
+        fence_after_sync();
+        stamp();  // 16: FFN-out complete
+        float y[2][32];
         float sum = 0.f;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           const int c = grp + 2 * t;
-          load_acc(ACC0, c);
-          const float* b = prm + kP_B3 + c * 32;
+          load_acc(EH, c, y[t]);
+          load_acc(EL, c, v);
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float hh[4] = {h[t][u].x, h[t][u].y, h[t][u].z, h[t][u].w};
+          for (int i = 0; i < 32; ++i) y[t][i] += v[i];
+          load_acc(ACC0, c, v);
+          const float* b = prm + kP_BOUT + c * 32;
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              const int i = u * 4 + q4;
-              v[i] = hh[q4] + (on ? v[i] + b[i] : 0.f);
-              sum += v[i];
-            }
-          }
-          store_tmem(ACC0 + c * 32, v);
+          for (int i = 0; i < 32; ++i) { y[t][i] += v[i] + b[i]; sum += y[t][i]; }
         }
-        tmem_st_wait();
-        const float mean = row_total(sum, 0) * (1.f / 128.f);
+        const float mean3 = row_total(sum, 2) * (1.f / 128.f);
         float var = 0.f;
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          load_acc(ACC0, grp + 2 * t);
+        for (int t = 0; t < 2; ++t)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) { float d = v[i] - mean; var += d * d; }
-        }
-        const float rstd = rsqrtf(row_total(var, 1) * (1.f / 128.f) + 1e-5f);
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int c = grp + 2 * t;
-          load_acc(ACC0, c);
-          const float* gm = prm + kP_LN2G + c * 32;
-          const float* bt = prm + kP_LN2B + c * 32;
-          float lo[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float e = (v[i] - mean) * rstd * gm[i] + bt[i];
-            split_tf32(e, v[i], lo[i]);
-          }
-          store_tmem(EH + c * 32, v);
-          store_tmem(EL + c * 32, lo);
-        }
-        tmem_st_wait();
-        fence_before_sync();
-        mbar_arrive(wk_done);
-      }
-      // ---- FFN: hidden slice j = relu(acc + b_in[j])  -> A operand of the matching FFN-out slice
-      for (int j = 0; j < 4; ++j) {
-        mbar_wait(&acc_full[1], accph[1]); accph[1] ^= 1;
-        fence_after_sync();
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int c = grp + 2 * t;
-          load_acc(ACC1, c);
-          const float* b = prm + kP_BIN + j * 128 + c * 32;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + b[i], 0.f);
-          publish(14 + 4 * j + c, v, kKC);
-        }
-        if (j < 3) {
-          fence_before_sync();
-          mbar_arrive(wk_done);
-        }
-      }
-      // ---- final: y = LN3(e + acc + b_out) * mask   (layers.py:143-146)
-      mbar_wait(&acc_full[0], accph[0]); accph[0] ^= 1;
-      fence_after_sync();
-      float sum = 0.f;
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int c = grp + 2 * t;
-        float eh[32];
-        load_acc(EH, c);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) eh[i] = v[i];
-        load_acc(EL, c);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) eh[i] += v[i];
-        load_acc(ACC0, c);
-        const float* b = prm + kP_BOUT + c * 32;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { v[i] = eh[i] + v[i] + b[i]; sum += v[i]; }
-        store_tmem(ACC0 + c * 32, v);
-      }
-      tmem_st_wait();
-      const float mean3 = row_total(sum, 2) * (1.f / 128.f);
-      float var = 0.f;
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        load_acc(ACC0, grp + 2 * t);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { float d = v[i] - mean3; var += d * d; }
-      }
-      const float rstd3 = rsqrtf(row_total(var, 3) * (1.f / 128.f) + 1e-5f);
-      float* orow = a.out + ((size_t)rr * K + (in_range ? k : 0)) * 128;
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int c = grp + 2 * t;
-        load_acc(ACC0, c);
-        const float* gm = prm + kP_LN3G + c * 32;
-        const float* bt = prm + kP_LN3B + c * 32;
+          for (int i = 0; i < 32; ++i) { float d = y[t][i] - mean3; var += d * d; }
+        const float rstd3 = rsqrtf(row_total(var, 3) * (1.f / 128.f) + 1e-5f);
+        float* orow = a.out + ((size_t)rr * K + (in_range ? k : 0)) * 128;
         if (in_range) {
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            float4 y;
-            const int i = u * 4;
-            y.x = on ? (v[i + 0] - mean3) * rstd3 * gm[i + 0] + bt[i + 0] : 0.f;
-            y.y = on ? (v[i + 1] - mean3) * rstd3 * gm[i + 1] + bt[i + 1] : 0.f;
-            y.z = on ? (v[i + 2] - mean3) * rstd3 * gm[i + 2] + bt[i + 2] : 0.f;
-            y.w = on ? (v[i + 3] - mean3) * rstd3 * gm[i + 3] + bt[i + 3] : 0.f;
-            *reinterpret_cast<float4*>(orow + c * 32 + i) = y;
+          for (int t = 0; t < 2; ++t) {
+            const int c = grp + 2 * t;
+            const float* gm = prm + kP_LN3G + c * 32;
+            const float* bt = prm + kP_LN3B + c * 32;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              float4 o;
+              const int i = u * 4;
+              o.x = on ? (y[t][i + 0] - mean3) * rstd3 * gm[i + 0] + bt[i + 0] : 0.f;
+              o.y = on ? (y[t][i + 1] - mean3) * rstd3 * gm[i + 1] + bt[i + 1] : 0.f;
+              o.z = on ? (y[t][i + 2] - mean3) * rstd3 * gm[i + 2] + bt[i + 2] : 0.f;
+              o.w = on ? (y[t][i + 3] - mean3) * rstd3 * gm[i + 3] + bt[i + 3] : 0.f;
+              *reinterpret_cast<float4*>(orow + c * 32 + i) = o;
+            }
           }
         }
       }
-    }
-    // end of tile: both accumulators and the FFN operand have been fully read by this thread
-    fence_before_sync();
-    mbar_arrive(wk_done);
-    qbase += EDGE ? 30 : 10;
+      stamp();  // 17 (edge) / 5 (node): outputs written
+      // end of tile: both accumulators and the FFN operand have been fully read by this thread
+      fence_before_sync();
+      mbar_arrive(wk_done);
+      qbase += EDGE ? 30 : 10;
+      cx = nx;
     }  // tile loop
   }
 
@@ -589,6 +652,14 @@ using namespace pp;
 
 extern "C" int64_t pp_tc_stream_floats() { return tc::kStreamFloats; }
 
+static unsigned long long* g_tc_trace = nullptr;
+// Diagnostics: subsequent pp_ipmp_edge_tc launches record clock64() stamps of the first tile of CTA 0 (one worker
+// thread, phase boundaries, see the stamp() calls in edge_tc_kernel) into `trace` (device, >= 32 entries); NULL = off.
+extern "C" int pp_set_tc_trace(uint64_t* trace) {
+  g_tc_trace = reinterpret_cast<unsigned long long*>(trace);
+  return 0;
+}
+
 // Tensor-core version of pp_ipmp_edge_node (path = 0) and pp_ipmp_edge_edge (path = 1).
 //   wstream: operand images of this layer and path, pp_tc_stream_floats() floats (weights.py: pack_tc_stream)
 //   passes : 3 = split TF32 (fp32-grade), 1 = plain TF32;  cluster: 1, 2 or 4 CTAs sharing the weight stream
@@ -615,6 +686,7 @@ extern "C" int pp_ipmp_edge_tc(const float* weights, int64_t layer, int64_t path
   a.hE_in = hE_in; a.he_shared = (int)he_shared;
   a.A = wsA; a.Nn = wsN; a.pglob = wsP;
   a.out = out;
+  a.trace = g_tc_trace;
   int rc;
 #define PP_TC_CASE(E, P, C) if (path == (E) && passes == (P) && cluster == (C)) rc = tc::launch<(E) != 0, P, C>(a, stream); else
   PP_TC_CASE(0, 3, 1) PP_TC_CASE(0, 3, 2) PP_TC_CASE(0, 3, 4) PP_TC_CASE(0, 1, 1) PP_TC_CASE(0, 1, 2) PP_TC_CASE(0, 1, 4)

@@ -173,7 +173,8 @@ def pack_tc_stream(sd, stream_floats):
     Per (layer, path) the chunks follow the kernel's consumption order, each chunk = hi image then lo image:
       G1: W_in[:, h_E | pair geometry]  k = 0..167 in chunks of 32, 32, 32, 32, 32, 8
       G2: W_inter.0 (4 chunks), G3: W_out (4 chunks)
-      for j in 0..3:  FFN-in rows 128j..128j+127 (4 chunks), FFN-out columns 128j..128j+127 (4 chunks)
+      FFN slices j = 0..3 (FFN-in = rows 128j..128j+127 of edge_dense.W_in, FFN-out = columns 128j..128j+127 of
+      edge_dense.W_out, 4 chunks each), software-pipelined by one slice: in0, in1, out0, in2, out1, in3, out2, out3
     The node path (path 0) uses G1 and G2 of node_message_fn only; the rest of its stream is zero."""
     check_state_dict(sd)
     f = {k: v.detach().to("cpu", torch.float32) for k, v in sd.items()}
@@ -186,8 +187,10 @@ def pack_tc_stream(sd, stream_floats):
             if path == 1:
                 mats.append(f[p + fn + ".W_out.weight"])
                 Fi, Fo = f[p + "edge_dense.W_in.weight"], f[p + "edge_dense.W_out.weight"]
+                mats.append(Fi[0:128, :])
                 for j in range(4):
-                    mats.append(Fi[128 * j:128 * (j + 1), :])
+                    if j + 1 < 4:
+                        mats.append(Fi[128 * (j + 1):128 * (j + 2), :])
                     mats.append(Fo[:, 128 * j:128 * (j + 1)])
             pieces = []
             for M in mats:
