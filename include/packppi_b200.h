@@ -43,6 +43,14 @@ int64_t pp_table_stride(void); /* floats per residue-type table record */
 int pp_knn_build(const float* X, const float* residue_mask, int64_t B, int64_t L, int64_t K, int64_t* E_idx,
                  int32_t* nbr, float* D_neighbors, float* mask_attend, float* msum, pp_stream_t stream);
 
+/* Cell-list version of pp_knn_build: same arguments and bit-identical outputs, O(L * neighbourhood) instead of O(L^2)
+ * (cells of >= 7 A on CA, warp-level top-K, ring expansion until the K-th neighbour is closer than the searched cube).
+ * ws_int: B * 2 * (pp_knn_cells_max() + 1) + B * L int32; ws_box: B * 8 floats. */
+int64_t pp_knn_cells_max(void);
+int pp_knn_build_cells(const float* X, const float* residue_mask, int64_t B, int64_t L, int64_t K, int64_t* E_idx,
+                       int32_t* nbr, float* D_neighbors, float* mask_attend, float* msum, int32_t* ws_int,
+                       float* ws_box, pp_stream_t stream);
+
 /* Rigid.from_3_points(N,CA,C) (utils/rigid_utils.py:1126-1179, fixed=True) and _impute_CB (encoder.py:137-142).
  * geo [G][pp_geo_stride()]: R(9, row-major) t(3) N CA C O CB(15). */
 int pp_geometry_build(const float* X, int64_t G, float* geo, pp_stream_t stream);

@@ -17,6 +17,7 @@ _P, _I, _F = ctypes.c_void_p, ctypes.c_int64, ctypes.c_float
 # name -> argument kinds in header order: p = device pointer, i = int64, f = float, s = stream
 SIGNATURES = {
     "pp_knn_build": "pp" "iii" "ppppp" "s",
+    "pp_knn_build_cells": "pp" "iii" "ppppp" "pp" "s",
     "pp_geometry_build": "p" "i" "p" "s",
     "pp_edge_embed": "ppppp" "ii" "p" "s",
     "pp_node_embed": "ppppppp" "iii" "p" "s",
@@ -39,7 +40,7 @@ _KIND = {"p": _P, "i": _I, "f": _F, "s": _P}
 _lib = None
 
 # kernels launched per entry point (pp_ipmp_layer: 3, or 5 with the edge update - the caller passes `kernels=`)
-KERNELS = {"pp_knn_build": 1, "pp_geometry_build": 1, "pp_edge_embed": 1, "pp_node_embed": 1, "pp_ipmp_layer": 5,
+KERNELS = {"pp_knn_build": 1, "pp_knn_build_cells": 5, "pp_geometry_build": 1, "pp_edge_embed": 1, "pp_node_embed": 1, "pp_ipmp_layer": 5,
            "pp_ipmp_node_pre": 1, "pp_ipmp_edge_node": 1, "pp_ipmp_node_post": 1, "pp_ipmp_edge_edge": 1, "pp_ipmp_edge_tc": 1,
            "pp_decode_step": 1, "pp_atom14_fwd": 1, "pp_clash_neighbours": 1, "pp_clash_fwd_bwd": 2,
            "pp_prox_init": 4, "pp_prox_step": 3, "pp_selftest_umma": 1}
@@ -57,7 +58,8 @@ def load():
     lib = ctypes.CDLL(LIB_PATH)
     lib.pp_last_error.restype = ctypes.c_char_p
     lib.pp_abi_version.restype = ctypes.c_int
-    for fn in ("pp_layout_count", "pp_layout_total_floats", "pp_geo_stride", "pp_table_stride", "pp_tc_stream_floats"):
+    for fn in ("pp_layout_count", "pp_layout_total_floats", "pp_geo_stride", "pp_table_stride", "pp_tc_stream_floats",
+               "pp_knn_cells_max"):
         getattr(lib, fn).restype = _I
     lib.pp_prox_partial_floats.restype = _I
     lib.pp_prox_partial_floats.argtypes = [_I]

@@ -14,6 +14,8 @@ SIGMA_MIN, SIGMA_MAX = 0.01 * np.pi, np.pi  # schedule.py:148-149 defaults
 TOP_K = 32
 # Below this many residue rows (S*G) a denoising step is launch-latency bound (17 launches, ~0.1 ms of device work),
 # so repeated sampling on buffers of the same shape replays one captured CUDA graph of the whole 30-step loop.
+# From this many residues per complex the kNN graph is built with the cell-list kernel instead of the O(L^2) scan.
+CELL_LIST_MIN_L = int(os.environ.get("PACKPPI_B200_CELL_LIST_MIN_L", "1024"))
 GRAPH_ROWS_MAX = int(os.environ.get("PACKPPI_B200_GRAPH_ROWS", "16384"))
 
 
@@ -63,6 +65,7 @@ class Graph:
         self.K = min(top_k, self.L)
         self.X = _f32(X, dev).clone()
         self.mask = _f32(residue_mask, dev).clone()
+        self._cells = None
         self._replay = {}  # captured CUDA graphs of the sampling loop, keyed by (S, steps, ...)
         self._seen = set()
         G, K = self.G, self.K
@@ -76,8 +79,15 @@ class Graph:
         self._build()
 
     def _build(self):
-        _lib.call("pp_knn_build", self.X, self.mask, self.B, self.L, self.K, self.E_idx, self.nbr, self.D_neighbors,
-                  self.mask_attend, self.msum)
+        outs = (self.E_idx, self.nbr, self.D_neighbors, self.mask_attend, self.msum)
+        if self.L >= CELL_LIST_MIN_L:  # cell list: O(L * neighbourhood); identical output
+            if self._cells is None:
+                nc = int(_lib.load().pp_knn_cells_max()) + 1
+                self._cells = (torch.empty(self.B * 2 * nc + self.G, dtype=torch.int32, device=self.X.device),
+                               torch.empty(self.B * 8, dtype=torch.float32, device=self.X.device))
+            _lib.call("pp_knn_build_cells", self.X, self.mask, self.B, self.L, self.K, *outs, *self._cells)
+        else:
+            _lib.call("pp_knn_build", self.X, self.mask, self.B, self.L, self.K, *outs)
         _lib.call("pp_geometry_build", self.X, self.G, self.geo)
 
     def rebuild(self, X, residue_mask):

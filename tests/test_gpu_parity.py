@@ -66,6 +66,56 @@ def test_knn_bit_exact(case, model, dev):
     assert torch.equal(E.cpu(), mo.knn_graph(b.X[:, :, 1, :], b.residue_mask)[1])
 
 
+def _knn_both(X, mask, dev):
+    from packppi_b200 import _lib
+    B, L = X.shape[:2]
+    K = min(32, L)
+    nc = int(_lib.load().pp_knn_cells_max()) + 1
+    out = []
+    for cells in (False, True):
+        E = torch.empty(B, L, K, dtype=torch.int64, device=dev)
+        nbr = torch.empty(B * L, K, dtype=torch.int32, device=dev)
+        D = torch.empty(B, L, K, device=dev)
+        ma = torch.empty(B * L, K, device=dev)
+        ms = torch.empty(B * L, device=dev)
+        if cells:
+            wi = torch.empty(B * 2 * nc + B * L, dtype=torch.int32, device=dev)
+            wb = torch.empty(B * 8, device=dev)
+            _lib.call("pp_knn_build_cells", X, mask, B, L, K, E, nbr, D, ma, ms, wi, wb)
+        else:
+            _lib.call("pp_knn_build", X, mask, B, L, K, E, nbr, D, ma, ms)
+        out.append((E, nbr, D, ma, ms))
+    return out
+
+
+@pytest.mark.parametrize("case", ["syn5", "syn33", "synbatch", "t1124"])
+def test_knn_cell_list_equals_scan_on_fixtures(case, dev):
+    _, b = load_golden(case)
+    a, c = _knn_both(b.X.to(dev).contiguous(), b.residue_mask.to(dev).contiguous(), dev)
+    for x, y in zip(a, c):
+        assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("chains,seed", [((500,) * 10, 5000), ((700, 650, 150), 7), ((40, 30), 9)])
+def test_knn_cell_list_equals_scan_synthetic(chains, seed, dev):
+    """Full size (5000 residues), a padded batch with masked residues, an elongated one: bit-identical outputs."""
+    from packppi_b200 import collate, synthetic
+    b1 = synthetic.make_complex(chains, seed=seed)
+    b2 = synthetic.make_complex(tuple(max(5, c // 2) for c in chains), seed=seed + 1)
+    b2["X"][0, :, :, 0] *= 3.0  # stretch along x: non-cubic grid
+    b = collate([b1, b2])
+    mask = b.residue_mask.clone()
+    mask[0, 3] = 0
+    mask[0, 17:25] = 0
+    X = b.X * mask[..., None, None]
+    a, c = _knn_both(X.to(dev).contiguous(), mask.to(dev).contiguous(), dev)
+    for x, y in zip(a, c):
+        assert torch.equal(x, y)
+    from oracle import msc_oracle as mo
+    if X.shape[1] <= 2000:
+        assert torch.equal(c[0].cpu(), mo.knn_graph(X[:, :, 1, :], mask)[1])
+
+
 @pytest.mark.parametrize("case", ALL_CASES)
 def test_network_probe(case, model, dev):
     g, b = load_golden(case)
