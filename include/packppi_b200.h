@@ -129,6 +129,16 @@ int pp_clash_neighbours(const float* tables, const float* X, const int64_t* resi
                         const int64_t* residue_index, int64_t B, int64_t L, float cutoff, int64_t fill, float* reach,
                         int32_t* counts, const int64_t* start, int32_t* list, pp_stream_t stream);
 
+/* Spatially hashed version: pp_clash_reach computes reach [G]; pp_clash_neighbours_cells bins the residues into cells
+ * of edge h_min >= 2 * max(reach) + cutoff and searches the 27 surrounding cells (same counts and list as
+ * pp_clash_neighbours, ascending order).  fill = 0 bins and counts, fill = 1 reuses the bins and writes the list.
+ * Workspaces as for pp_knn_build_cells. */
+int pp_clash_reach(const float* tables, const float* X, const int64_t* residue_type, const float* atom_exists,
+                   int64_t G, float* reach, pp_stream_t stream);
+int pp_clash_neighbours_cells(const float* X, const float* reach, const int64_t* residue_index, int64_t B, int64_t L,
+                              float cutoff, float h_min, int64_t fill, int32_t* counts, const int64_t* start,
+                              int32_t* list, int32_t* ws_int, float* ws_box, pp_stream_t stream);
+
 /* compute_residue_clash (models/components/clash.py:335-365) and its gradient.
  * lower/upper [21][14][14] from make_atom14_dists_bounds (utils/residue_constants.py:809-869).
  * mode 0: per_res [S*G].  mode 1: also grad_chi [S*G][4] = d(sum_r res_w[r] per_res[r]) / d chi (analytic).

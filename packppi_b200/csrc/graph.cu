@@ -107,13 +107,13 @@ struct CellBox {
   int nx, ny, nz;
 };
 
-__global__ void cell_box_kernel(const float* __restrict__ X, const float* __restrict__ mask, int L, CellBox* __restrict__ box,
-                                int* __restrict__ counts /*[B][kCellsMax+1]*/) {
+__global__ void cell_box_kernel(const float* __restrict__ X, const float* __restrict__ mask, int L, float h_min,
+                                CellBox* __restrict__ box, int* __restrict__ counts /*[B][kCellsMax+1]*/) {
   const int b = blockIdx.x;
   __shared__ float red[6][32];
   float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
   for (int j = threadIdx.x; j < L; j += blockDim.x) {
-    if (mask[(size_t)b * L + j] != 0.f) {
+    if (mask[(size_t)b * L + j] > 0.f) {
       const float* p = X + ((size_t)b * L + j) * 42 + 3;
       for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], p[k]); hi[k] = fmaxf(hi[k], p[k]); }
     }
@@ -130,7 +130,7 @@ __global__ void cell_box_kernel(const float* __restrict__ X, const float* __rest
       for (int w = 0; w < nw; ++w) { lo[k] = fminf(lo[k], red[k][w]); hi[k] = fmaxf(hi[k], red[3 + k][w]); }
     CellBox bx;
     if (lo[0] > hi[0]) { lo[0] = lo[1] = lo[2] = 0.f; hi[0] = hi[1] = hi[2] = 0.f; }  // no valid residue
-    float h = 7.f;
+    float h = h_min;
     for (;;) {
       bx.nx = (int)floorf((hi[0] - lo[0]) / h) + 1;
       bx.ny = (int)floorf((hi[1] - lo[1]) / h) + 1;
@@ -155,7 +155,7 @@ __device__ __forceinline__ int cell_of(const CellBox& bx, const float* p, int& c
 __global__ void cell_count_kernel(const float* __restrict__ X, const float* __restrict__ mask, int B, int L,
                                   const CellBox* __restrict__ box, int* __restrict__ counts) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= B * L || mask[r] == 0.f) return;
+  if (r >= B * L || !(mask[r] > 0.f)) return;
   int b = r / L, cx, cy, cz;
   int c = cell_of(box[b], X + (size_t)r * 42 + 3, cx, cy, cz);
   atomicAdd(&counts[(size_t)b * (kCellsMax + 1) + c + 1], 1);  // shifted by one: the scan turns it into cell starts
@@ -194,7 +194,7 @@ __global__ void cell_scan_kernel(int* __restrict__ counts, int* __restrict__ cur
 __global__ void cell_fill_kernel(const float* __restrict__ X, const float* __restrict__ mask, int B, int L,
                                  const CellBox* __restrict__ box, int* __restrict__ cursor, int* __restrict__ order) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= B * L || mask[r] == 0.f) return;
+  if (r >= B * L || !(mask[r] > 0.f)) return;
   int b = r / L, cx, cy, cz;
   int c = cell_of(box[b], X + (size_t)r * 42 + 3, cx, cy, cz);
   int slot = atomicAdd(&cursor[(size_t)b * (kCellsMax + 1) + c], 1);
@@ -287,6 +287,78 @@ __global__ void knn_cells_kernel(const float* __restrict__ X, const float* __res
   if (msum && lane == 0) msum[warp] = ma / (float)K;
 }
 
+// Residue neighbour list of the clash term from the same cell list (cells of edge >= 2 * max reach + cutoff, so the
+// 27 surrounding cells contain every partner): candidates are marked in a per-warp bitmask in shared memory and then
+// emitted in ascending index order, which keeps the summation order of the pair kernel fixed from run to run.
+__global__ void clash_nbr_cells_kernel(const float* __restrict__ X, const float* __restrict__ reach,
+                                       const long long* __restrict__ residue_index, int B, int L, float cutoff,
+                                       const CellBox* __restrict__ box, const int* __restrict__ cell_start,
+                                       const int* __restrict__ order, int fill, int* __restrict__ count,
+                                       const long long* __restrict__ start, int* __restrict__ list) {
+  extern __shared__ unsigned bits_all[];
+  const int words = (L + 31) >> 5;
+  unsigned* bits = bits_all + (threadIdx.x >> 5) * words;
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= B * L) return;
+  const int b = warp / L;
+  const float ri = reach[warp];
+  int n = 0;
+  if (ri >= 0.f) {
+    for (int w = lane; w < words; w += 32) bits[w] = 0u;
+    __syncwarp();
+    const float* pi = X + (size_t)warp * 42 + 3;
+    const float xi = pi[0], yi = pi[1], zi = pi[2];
+    const long long idx_i = residue_index[warp];
+    const CellBox bx = box[b];
+    const int* cs = cell_start + (size_t)b * (kCellsMax + 1);
+    const int* ord = order + (size_t)b * L;
+    int cx, cy, cz;
+    cell_of(bx, pi, cx, cy, cz);
+    for (int dz = -1; dz <= 1; ++dz) {
+      int z = cz + dz;
+      if (z < 0 || z >= bx.nz) continue;
+      for (int dy = -1; dy <= 1; ++dy) {
+        int y = cy + dy;
+        if (y < 0 || y >= bx.ny) continue;
+        int x0 = max(cx - 1, 0), x1 = min(cx + 1, bx.nx - 1);
+        int row = (z * bx.ny + y) * bx.nx;
+        int s = cs[row + x0], e = cs[row + x1 + 1];
+        for (int t = s + lane; t < e; t += 32) {
+          int j = ord[t];
+          int gj = b * L + j;
+          float rj = reach[gj];
+          if (residue_index[gj] != idx_i) {  // clash.py:166-169: strict '<' on the index VALUE, both ways
+            const float* pj = X + (size_t)gj * 42 + 3;
+            float dx = pj[0] - xi, dy2 = pj[1] - yi, dz2 = pj[2] - zi;
+            float lim = ri + rj + cutoff;
+            if (dx * dx + dy2 * dy2 + dz2 * dz2 < lim * lim) atomicOr(&bits[j >> 5], 1u << (j & 31));
+          }
+        }
+      }
+    }
+    __syncwarp();
+    const long long base = fill ? start[warp] : 0;
+    for (int w0 = 0; w0 < words; w0 += 32) {
+      int w = w0 + lane;
+      unsigned v = (w < words) ? bits[w] : 0u;
+      int c = __popc(v);
+      int incl = c;
+      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      if (fill) {
+        int pos = n + incl - c;
+        while (v) {
+          int bit = __ffs(v) - 1;
+          v &= v - 1;
+          list[base + pos++] = b * L + (w << 5) + bit;
+        }
+      }
+      n += __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
+  if (!fill && lane == 0) count[warp] = n;
+}
+
 // Per-residue geometry record (PP_GEO_STRIDE floats): backbone frame R (row-major 3x3, columns e0 e1 e2), origin CA,
 // then N, CA, C, O and the virtual CB used by the edge features.
 __global__ void geometry_kernel(const float* __restrict__ X, int G, float* __restrict__ geo) {
@@ -355,13 +427,45 @@ extern "C" int pp_knn_build_cells(const float* X, const float* residue_mask, int
   int* cursor = counts + B * (pp::kCellsMax + 1);
   int* order = cursor + B * (pp::kCellsMax + 1);
   const int G = (int)(B * L);
-  pp::cell_box_kernel<<<(unsigned)B, 256, 0, stream>>>(X, residue_mask, (int)L, box, counts);
+  pp::cell_box_kernel<<<(unsigned)B, 256, 0, stream>>>(X, residue_mask, (int)L, 7.f, box, counts);
   pp::cell_count_kernel<<<(G + 255) / 256, 256, 0, stream>>>(X, residue_mask, (int)B, (int)L, box, counts);
   pp::cell_scan_kernel<<<(unsigned)B, 1024, 0, stream>>>(counts, cursor);
   pp::cell_fill_kernel<<<(G + 255) / 256, 256, 0, stream>>>(X, residue_mask, (int)B, (int)L, box, cursor, order);
   pp::knn_cells_kernel<<<(unsigned)(((long long)G * 32 + 255) / 256), 256, 0, stream>>>(
       X, residue_mask, (int)B, (int)L, (int)K, box, counts, order, (long long*)E_idx, nbr, D_neighbors, mask_attend, msum);
   return pp::check_launch("pp_knn_build_cells");
+}
+
+// Cell-list version of pp_clash_neighbours (same counts / list).  `reach` [B*L] comes from pp_clash_reach;
+// h_min >= 2 * max(reach) + cutoff.  fill = 0 bins the residues and counts; fill = 1 reuses the bins and writes the list.
+extern "C" int pp_clash_neighbours_cells(const float* X, const float* reach, const int64_t* residue_index, int64_t B,
+                                         int64_t L, float cutoff, float h_min, int64_t fill, int32_t* counts,
+                                         const int64_t* start, int32_t* list, int32_t* ws_int, float* ws_box,
+                                         cudaStream_t stream) {
+  PP_REQUIRE(X && reach && residue_index && ws_int && ws_box, "null pointer");
+  PP_REQUIRE(B > 0 && L > 0 && B * L < (1ll << 31), "bad sizes");
+  PP_REQUIRE(fill ? (start && list) : (counts != nullptr), "missing output for this pass");
+  PP_REQUIRE(h_min > 0.f, "h_min must be positive");
+  pp::CellBox* box = reinterpret_cast<pp::CellBox*>(ws_box);
+  int* cstart = ws_int;
+  int* cursor = cstart + B * (pp::kCellsMax + 1);
+  int* order = cursor + B * (pp::kCellsMax + 1);
+  const int G = (int)(B * L);
+  if (!fill) {
+    pp::cell_box_kernel<<<(unsigned)B, 256, 0, stream>>>(X, reach, (int)L, h_min, box, cstart);
+    pp::cell_count_kernel<<<(G + 255) / 256, 256, 0, stream>>>(X, reach, (int)B, (int)L, box, cstart);
+    pp::cell_scan_kernel<<<(unsigned)B, 1024, 0, stream>>>(cstart, cursor);
+    pp::cell_fill_kernel<<<(G + 255) / 256, 256, 0, stream>>>(X, reach, (int)B, (int)L, box, cursor, order);
+  }
+  const int warps_per_block = 4;
+  const size_t smem = (size_t)warps_per_block * ((L + 31) / 32) * 4;
+  PP_REQUIRE(smem <= 200 * 1024, "complex too long for the bitmask neighbour kernel");
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(pp::clash_nbr_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  pp::clash_nbr_cells_kernel<<<(unsigned)((G + warps_per_block - 1) / warps_per_block), warps_per_block * 32, smem,
+                               stream>>>(X, reach, (const long long*)residue_index, (int)B, (int)L, cutoff, box, cstart,
+                                         order, (int)fill, counts, (const long long*)start, list);
+  return pp::check_launch("pp_clash_neighbours_cells");
 }
 
 extern "C" int pp_geometry_build(const float* X, int64_t G, float* geo, cudaStream_t stream) {

@@ -441,6 +441,16 @@ extern "C" int pp_clash_neighbours(const float* tables, const float* X, const in
   return check_launch("pp_clash_neighbours");
 }
 
+// reach [G] of every residue (bound on |CA - atom| over all chi; -1 if the residue has no atoms).
+extern "C" int pp_clash_reach(const float* tables, const float* X, const int64_t* residue_type, const float* atom_exists,
+                              int64_t G, float* reach, cudaStream_t stream) {
+  PP_REQUIRE(tables && X && residue_type && atom_exists && reach, "null pointer");
+  PP_REQUIRE(G > 0, "bad sizes");
+  clash_reach_kernel<<<(unsigned)((G + 127) / 128), 128, 0, stream>>>(tables, X, (const long long*)residue_type,
+                                                                     atom_exists, (int)G, reach);
+  return check_launch("pp_clash_reach");
+}
+
 // mode 0: per_res only.  mode 1: per_res and grad_chi = d(sum_r res_w[r] * per_res[r]) / d chi.
 // Workspaces: atoms4 [S*G][14] float4, axes [S*G][4][6], bound [S*G].
 extern "C" int pp_clash_fwd_bwd(const float* tables, const float* lower, const float* upper, const float* X,

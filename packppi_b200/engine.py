@@ -309,13 +309,27 @@ class ClashContext:
         G = self.G
         self.reach = torch.empty(G, dtype=torch.float32, device=dev)
         counts = torch.empty(G, dtype=torch.int32, device=dev)
-        args = (self.tables.geo, self.X, self.rtype, self.exists, self.ridx, self.B, self.L, self.max_cut)
-        _lib.call("pp_clash_neighbours", *args, 0, self.reach, counts, None, None)
         self.start = torch.zeros(G + 1, dtype=torch.int64, device=dev)
-        self.start[1:] = torch.cumsum(counts.to(torch.int64), 0)
-        total = int(self.start[-1].item())  # one host sync per complex, not per step
-        self.list = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
-        _lib.call("pp_clash_neighbours", *args, 1, self.reach, None, self.start, self.list)
+        if self.L >= CELL_LIST_MIN_L:
+            # spatially hashed: bin the residues on CA, search the 27 surrounding cells
+            _lib.call("pp_clash_reach", self.tables.geo, self.X, self.rtype, self.exists, G, self.reach)
+            nc = int(_lib.load().pp_knn_cells_max()) + 1
+            wi = torch.empty(self.B * 2 * nc + G, dtype=torch.int32, device=dev)
+            wb = torch.empty(self.B * 8, dtype=torch.float32, device=dev)
+            h_min = 2.0 * float(self.reach.max().item()) + self.max_cut + 1e-3
+            args = (self.X, self.reach, self.ridx, self.B, self.L, self.max_cut, h_min)
+            _lib.call("pp_clash_neighbours_cells", *args, 0, counts, None, None, wi, wb)
+            self.start[1:] = torch.cumsum(counts.to(torch.int64), 0)
+            total = int(self.start[-1].item())  # one host sync per complex, not per step
+            self.list = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+            _lib.call("pp_clash_neighbours_cells", *args, 1, None, self.start, self.list, wi, wb, kernels=1)
+        else:
+            args = (self.tables.geo, self.X, self.rtype, self.exists, self.ridx, self.B, self.L, self.max_cut)
+            _lib.call("pp_clash_neighbours", *args, 0, self.reach, counts, None, None)
+            self.start[1:] = torch.cumsum(counts.to(torch.int64), 0)
+            total = int(self.start[-1].item())  # one host sync per complex, not per step
+            self.list = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+            _lib.call("pp_clash_neighbours", *args, 1, self.reach, None, self.start, self.list)
         self._ws = {}
         self._prox = {}
 

@@ -265,6 +265,19 @@ def test_state_dict_round_trip(model):
         assert torch.equal(v, sd[k].cpu())
 
 
+def test_clash_neighbour_list_hashed_equals_scan(dev, monkeypatch):
+    from packppi_b200 import engine, synthetic
+    b = _big(dev, (500,) * 4, 77)
+    lists = []
+    for min_l in (10 ** 9, 1):  # all-pairs scan, then cell list
+        monkeypatch.setattr(engine, "CELL_LIST_MIN_L", min_l)
+        cc = engine.ClashContext(dev, b.X, b.residue_type, b.atom_mask, b.residue_index)
+        lists.append((cc.start.clone(), cc.list.clone(), cc.reach.clone()))
+    for x, y in zip(*lists):
+        assert torch.equal(x, y)
+    assert int(lists[0][0][-1]) > 2000 * 10
+
+
 # ---------------------------------------------------------------------------------- full-size properties
 def _big(dev, chains, seed):
     from packppi_b200 import get_atom14_coords, synthetic
