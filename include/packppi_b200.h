@@ -165,7 +165,13 @@ int pp_prox_step(const float* tables, const float* lower, const float* upper, co
                  const int32_t* nbr_list, const float* sc_d, const uint8_t* mask, const float* z, float* x, float* m,
                  float* v, int64_t G, float tol, float max_cut, float lamda, float step_size, float bc2_sqrt,
                  float beta1, float beta2, float eps, float* snapshot, float* loss_out, float* per_res, float* atoms4,
-                 float* axes, float* bound, float* partial, pp_stream_t stream);
+                 float* axes, float* bound, float* partial, const uint8_t* owned, int64_t n_total, pp_stream_t stream);
+/* Slab-partitioned complex (one rank per slab): the arrays hold the rank's owned residues plus
+ * the halo; owned uint8 [G] (NULL = all) marks the residues this rank optimises and counts in loss_out, n_total is the
+ * residue count of the whole complex (0 = G).  pp_prox_init_from_mean builds mask / z / x from per_res and the
+ * all-reduced mean[1]. */
+int pp_prox_init_from_mean(const float* per_res, const float* mean, const float* sc_d, const uint8_t* owned, int64_t G,
+                           uint8_t* mask, float* z, float* x, float* m, float* v, pp_stream_t stream);
 
 /* Diagnostics: one 128 x 128 tile D = A W^T on the tcgen05 tensor cores (A [128][K], W [128][K], K % 32 == 0),
  * passes 1 = TF32, 3 = split TF32 (~fp32); ts_mode != 0 feeds A from tensor memory instead of shared memory.

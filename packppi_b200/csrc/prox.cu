@@ -211,6 +211,7 @@ struct AdamArgs {
   const float* sc_d;    // [R][4] starting angles
   const unsigned char* mask;  // [R][4] clash mask
   float* snapshot;      // [R][4] where(mask, x_new, SC_D)
+  const unsigned char* owned;  // [R] or null: residues this rank owns (slab-partitioned complex); others are halo
   float step_size, bc2_sqrt, beta1, beta2, eps, inv_n;
 };
 
@@ -338,9 +339,10 @@ clash_pair_kernel(const float4* __restrict__ atoms, const float* __restrict__ bo
   float sc_term = 0.f;
   if (MODE == 2) {
     // f(x) = mean_res |x' - z|^2 + lamda * mean_res clash(x'),  x' = where(mask, x, SC_D)   (optimize.py:33-45)
+    const bool mine = ad.owned == nullptr || ad.owned[rr] != 0;
     if (live && lane16 < 4) {
       size_t o = (size_t)r * 4 + lane16;
-      bool mk = ad.mask[o] != 0;
+      bool mk = ad.mask[o] != 0 && mine;
       float x = ad.x[o], z = ad.z[o], s0 = ad.sc_d[o];
       float xp = mk ? x : s0;
       float diff = xp - z;
@@ -354,16 +356,18 @@ clash_pair_kernel(const float4* __restrict__ atoms, const float* __restrict__ bo
       ad.v[o] = v;
       ad.x[o] = xn;
       ad.snapshot[o] = mk ? xn : s0;
+      if (!mine) sc_term = 0.f;
     }
     sc_term += __shfl_xor_sync(0xffffffffu, sc_term, 1);
     sc_term += __shfl_xor_sync(0xffffffffu, sc_term, 2);
   }
+  const bool counted = (MODE != 2 || ad.owned == nullptr) ? true : (ad.owned[rr] != 0);
   if (partial) {
     // block partial sums (fixed order): [0] sum of per-residue clash, [1] sum of |x' - z|^2
     __shared__ float red[2][8];
     if (lane16 == 0) {
-      red[0][threadIdx.x >> 4] = live ? pr : 0.f;
-      red[1][threadIdx.x >> 4] = live ? sc_term : 0.f;
+      red[0][threadIdx.x >> 4] = (live && counted) ? pr : 0.f;
+      red[1][threadIdx.x >> 4] = (live && counted) ? sc_term : 0.f;
     }
     __syncthreads();
     if (threadIdx.x < 2) {
@@ -395,11 +399,11 @@ __global__ void prox_reduce_kernel(const float* __restrict__ partial, int nblock
 
 // mask = per_res > mean(per_res), expanded to the 4 chi; z = SC_D * mask; x = z; m = v = 0   (optimize.py:5-31,47)
 __global__ void prox_init_kernel(const float* __restrict__ per_res, const float* __restrict__ mean, const float* __restrict__ sc_d,
-                                 int R, unsigned char* __restrict__ mask, float* __restrict__ z, float* __restrict__ x,
-                                 float* __restrict__ m, float* __restrict__ v) {
+                                 int R, const unsigned char* __restrict__ owned, unsigned char* __restrict__ mask,
+                                 float* __restrict__ z, float* __restrict__ x, float* __restrict__ m, float* __restrict__ v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R * 4) return;
-  bool mk = per_res[i >> 2] > mean[1];
+  bool mk = per_res[i >> 2] > mean[1] && (owned == nullptr || owned[i >> 2] != 0);
   mask[i] = mk;
   float zz = mk ? sc_d[i] : 0.f * sc_d[i];
   z[i] = zz;
@@ -503,8 +507,20 @@ extern "C" int pp_prox_init(const float* tables, const float* lower, const float
                                                    atom_exists, (const long long*)nbr_start, nbr_list, lower, upper, tables,
                                                    nullptr, 0.f, tol, max_cut, (int)G, 1, per_res, nullptr, ad, partial);
   prox_reduce_kernel<<<1, 256, 0, stream>>>(partial, (int)blocks, 1.f, 1.f / (float)G, mean_out);
-  prox_init_kernel<<<(unsigned)((G * 4 + 255) / 256), 256, 0, stream>>>(per_res, mean_out, sc_d, (int)G, mask, z, x, m, v);
+  prox_init_kernel<<<(unsigned)((G * 4 + 255) / 256), 256, 0, stream>>>(per_res, mean_out, sc_d, (int)G, nullptr, mask, z, x,
+                                                                        m, v);
   return check_launch("pp_prox_init");
+}
+
+// Slab-partitioned variant of the second half of pp_prox_init: per_res and mean[1] (the mean over the WHOLE complex,
+// all-reduced by the caller) are given; residues with owned == 0 are halo copies and are never optimised here.
+extern "C" int pp_prox_init_from_mean(const float* per_res, const float* mean, const float* sc_d, const uint8_t* owned,
+                                      int64_t G, uint8_t* mask, float* z, float* x, float* m, float* v,
+                                      cudaStream_t stream) {
+  PP_REQUIRE(per_res && mean && sc_d && mask && z && x && m && v, "null pointer");
+  PP_REQUIRE(G > 0, "bad sizes");
+  prox_init_kernel<<<(unsigned)((G * 4 + 255) / 256), 256, 0, stream>>>(per_res, mean, sc_d, (int)G, owned, mask, z, x, m, v);
+  return check_launch("pp_prox_init_from_mean");
 }
 
 // One proximal step (optimize.py:60-71): loss and gradient at the current x, Adam update, snapshot, loss value.
@@ -515,15 +531,15 @@ extern "C" int pp_prox_step(const float* tables, const float* lower, const float
                             float* m, float* v, int64_t G, float tol, float max_cut, float lamda, float step_size,
                             float bc2_sqrt, float beta1, float beta2, float eps, float* snapshot, float* loss_out,
                             float* per_res, float* atoms4, float* axes, float* bound, float* partial,
-                            cudaStream_t stream) {
+                            const uint8_t* owned, int64_t n_total, cudaStream_t stream) {
   PP_REQUIRE(tables && lower && upper && X && residue_type && atom_exists && nbr_start && nbr_list && sc_d, "null pointer");
   PP_REQUIRE(mask && z && x && m && v && snapshot && loss_out && per_res && atoms4 && axes && bound && partial, "null output");
   PP_REQUIRE(G > 0, "bad sizes");
   atom14_kernel<<<(unsigned)((G + 127) / 128), 128, 0, stream>>>(tables, X, (const long long*)residue_type, x, sc_d, mask,
                                                                 (int)G, 1, nullptr, atom_exists, (float4*)atoms4, axes,
                                                                 bound);
-  const float inv_n = 1.f / (float)G;
-  AdamArgs ad{x, m, v, z, sc_d, mask, snapshot, step_size, bc2_sqrt, beta1, beta2, eps, inv_n};
+  const float inv_n = 1.f / (float)(n_total > 0 ? n_total : G);  // mean over the residues of the WHOLE complex
+  AdamArgs ad{x, m, v, z, sc_d, mask, snapshot, owned, step_size, bc2_sqrt, beta1, beta2, eps, inv_n};
   unsigned blocks = (unsigned)((G + 7) / 8);
   clash_pair_kernel<2><<<blocks, 128, 0, stream>>>((const float4*)atoms4, bound, axes, X, (const long long*)residue_type,
                                                    atom_exists, (const long long*)nbr_start, nbr_list, lower, upper, tables,

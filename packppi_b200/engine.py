@@ -364,7 +364,7 @@ class ClashContext:
             bc2_sqrt = math.sqrt(1 - beta2 ** t)
             _lib.call("pp_prox_step", *static, st["mask"], st["z"], st["x"], st["m"], st["v"], G, self.tol,
                       self.max_cut, float(lamda), step_size, bc2_sqrt, beta1, beta2, eps, st["snaps"][k],
-                      st["losses"][k], st["per_res"], ws["atoms4"], ws["axes"], ws["bound"], st["partial"])
+                      st["losses"][k], st["per_res"], ws["atoms4"], ws["axes"], ws["bound"], st["partial"], None, 0)
 
     def proximal(self, sc_d, lamda, num_steps, lr=1e-2, beta1=0.9, beta2=0.999, eps=1e-8):
         """optimize.py:21-73 for one complex.  Returns (snapshots [num_steps,G,4], losses [num_steps], mask [G,4]);

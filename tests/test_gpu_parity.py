@@ -278,6 +278,19 @@ def test_clash_neighbour_list_hashed_equals_scan(dev, monkeypatch):
     assert int(lists[0][0][-1]) > 2000 * 10
 
 
+def test_slab_proximal_single_rank_equals_plain(dev):
+    """World size 1: the slab-partitioned driver (owned = everything, no halo) reproduces proximal_optimizer."""
+    from packppi_b200 import proximal_optimizer, shard
+    g, b = load_golden("syn300")
+    bd = b.to(dev)
+    start = tt(g["in_prox_start"]).to(dev)
+    snaps, losses = proximal_optimizer(bd, start, 12.0, 0.5, 1.0, 20)
+    sp = shard.SlabProximal(bd, 12.0, 0.5)
+    s2, l2 = sp.run(start, 1.0, 20)
+    assert torch.equal(torch.stack(snaps)[:, 0], s2)
+    np.testing.assert_allclose(l2.cpu().numpy(), np.asarray(losses), rtol=1e-6)
+
+
 # ---------------------------------------------------------------------------------- full-size properties
 def _big(dev, chains, seed):
     from packppi_b200 import get_atom14_coords, synthetic
