@@ -105,6 +105,12 @@ int pp_ipmp_edge_tc(const float* weights, int64_t layer, int64_t path, const flo
                     const float* hE_in, int64_t he_shared, const float* wsA, const float* wsN, const float* wsP,
                     float* out, int64_t passes, int64_t cluster, pp_stream_t stream);
 
+/* Tensor-core version of pp_ipmp_node_post (reference layers.py:127-132), same kernel family: tile = 128 residue
+ * rows.  wstream = operand images of path 2 of this layer; hV [S*G][128] is updated in place. */
+int pp_ipmp_node_post_tc(const float* weights, int64_t layer, const float* wstream, const float* msum,
+                         const float* residue_mask, int64_t G, int64_t K, int64_t S, const float* wsAcc, float* hV,
+                         int64_t passes, int64_t cluster, pp_stream_t stream);
+
 /* Diagnostics: later pp_ipmp_edge_tc launches write clock64() stamps of the phase boundaries of their first tile
  * (CTA 0, one worker thread) into trace (device memory, >= 32 uint64); NULL switches it off. */
 int pp_set_tc_trace(uint64_t* trace);

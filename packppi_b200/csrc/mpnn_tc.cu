@@ -61,6 +61,8 @@ struct Args {
   const float *B2, *B3, *LNG, *LNB, *BIN, *BOUT, *LN3G, *LN3B;
   const float* hE_in; int he_shared;
   const float *A, *Nn, *pglob;
+  const float *rmask, *msum, *hres;  // MODE 2: residue mask [G], mean attention mask [G], residual rows h_V [R][128]
+  float in_scale;                    // MODE 2: 1 / K applied to the summed messages
   float* out;             // node path: accsum [R][128]; edge path: hE_out [R][K][128]
   unsigned long long* trace;  // optional: clock64 stamps of CTA 0 / first tile (pp_set_tc_trace), else null
 };
@@ -120,8 +122,13 @@ __device__ __forceinline__ void ld32(const float* __restrict__ p, float (&d)[32]
   }
 }
 
-template <bool EDGE, int PASSES, int CLUSTER>
+// MODE 0: node message (G1, G2, masked sum over K)      tile = 4 residues x 32 edges
+// MODE 1: edge update  (G1, G2, G3, LN, FFN, LN)        tile = 4 residues x 32 edges
+// MODE 2: node epilogue (W3, LN0, FFN, LN1 per residue; reference layers.py:127-132)   tile = 128 residue rows
+template <int MODE, int PASSES, int CLUSTER>
 __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
+  constexpr bool EDGE = MODE != 0;   // runs the G3 / LayerNorm / FFN part
+  constexpr bool POST = MODE == 2;   // per-residue rows instead of per-edge rows, no G1 / G2
   extern __shared__ __align__(1024) uint8_t smem[];
   float* Aring = reinterpret_cast<float*>(smem);
   float* Bring = Aring + kSA * kSlotFloats;
@@ -138,11 +145,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int R = a.S * a.G, K = a.K;
-  const int ntiles = (R + 3) / 4;
+  const int ntiles = POST ? (R + kRows - 1) / kRows : (R + 3) / 4;
   // persistent CTAs: every CTA runs the same number of iterations (a cluster shares one weight stream in lockstep);
   // iterations past the last tile work on fully masked rows
   const int niter = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
-  constexpr int NCHUNK = EDGE ? kChunksEdge : kChunksNode;
   constexpr uint16_t kMask = (uint16_t)((1u << CLUSTER) - 1);
 
   if (tid == 0) {
@@ -157,7 +163,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
     const float* src[8] = {a.B2, a.B3, a.LNG, a.LNB, a.BIN, a.BOUT, a.LN3G, a.LN3B};
     const int off[9] = {kP_B2, kP_B3, kP_LN2G, kP_LN2B, kP_BIN, kP_BOUT, kP_LN3G, kP_LN3B, kParamFloats};
     for (int t = 0; t < 8; ++t)
-      if (EDGE || t == 0)
+      if ((EDGE || t == 0) && !(POST && t == 0))
         for (int i = tid; i < off[t + 1] - off[t]; i += kThreadsTC) prm[off[t] + i] = src[t][i];
   }
   if (warp == 8) tmem_alloc<512>(tmem_slot);
@@ -175,8 +181,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
       const uint32_t crank = (CLUSTER > 1) ? cluster_rank() : 0;
       for (int it = 0; it < niter; ++it) {
         const float* src = a.wstream;
+        constexpr int NCHUNK = POST ? 36 : (EDGE ? kChunksEdge : kChunksNode);
         for (int i = 0; i < NCHUNK; ++i) {
-          const int kc = (i == 5) ? 8 : kKC;
+          const int kc = (!POST && i == 5) ? 8 : kKC;
           for (int h = 0; h * kSubK < kc; ++h) {
             const int kcs = min(kSubK, kc - h * kSubK);
             const uint32_t img = (uint32_t)kRows * kcs * 4;
@@ -228,12 +235,14 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
         if (ss) { mma_commit(&a_empty[ra.idx]); ra.next(kSA); }
       };
       for (int it = 0; it < niter; ++it) {
-        // G1: [h_E | pair] (168) -> ACC0
-        for (int c = 0; c < 6; ++c) chunk(true, ACC0, 0, c == 5 ? 8 : kKC, c == 0);
-        mma_commit(&acc_full[0]);
-        // G2 -> ACC1
-        for (int c = 0; c < 4; ++c) chunk(true, ACC1, 0, kKC, c == 0);
-        mma_commit(&acc_full[1]);
+        if (!POST) {
+          // G1: [h_E | pair] (168) -> ACC0
+          for (int c = 0; c < 6; ++c) chunk(true, ACC0, 0, c == 5 ? 8 : kKC, c == 0);
+          mma_commit(&acc_full[0]);
+          // G2 -> ACC1
+          for (int c = 0; c < 4; ++c) chunk(true, ACC1, 0, kKC, c == 0);
+          mma_commit(&acc_full[1]);
+        }
         if (EDGE) {
           // G3 -> ACC0
           for (int c = 0; c < 4; ++c) chunk(true, ACC0, 0, kKC, c == 0);
@@ -279,7 +288,18 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
     };
     auto row_ctx = [&](int it) {
       RowCtx c;
-      c.r = (it * (int)gridDim.x + (int)blockIdx.x) * 4 + rl;
+      const int tile = it * (int)gridDim.x + (int)blockIdx.x;
+      if (POST) {  // one residue row per thread
+        c.r = tile * kRows + m;
+        c.in_range = c.r < R;
+        c.rr = min(c.r, R - 1);
+        c.g = c.rr % a.G;
+        c.on = c.in_range && a.rmask[c.g] != 0.f;
+        c.jrow = c.rr;
+        c.hrow = a.hE_in + (size_t)c.rr * 128;  // summed messages of the residue
+        return c;
+      }
+      c.r = tile * 4 + rl;
       c.in_range = c.r < R && k < K;
       c.rr = min(c.r, R - 1);
       const int s = c.rr / a.G;
@@ -348,8 +368,19 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
         tmem_st32(col + lane_base, u);
       };
 
-      // ---- first A operand: h_E row (chunks 0-3) and the pair geometry (chunk 4: 32 columns, chunk 5: 8 columns)
-      {
+      // ---- first A operand: h_E row (chunks 0-3) and the pair geometry (chunk 4: 32 columns, chunk 5: 8 columns);
+      //      node epilogue: the residue's summed messages scaled by 1/K (the mean over K commutes with W3)
+      if (POST) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            v[u * 4] = hpre[t][u].x * a.in_scale; v[u * 4 + 1] = hpre[t][u].y * a.in_scale;
+            v[u * 4 + 2] = hpre[t][u].z * a.in_scale; v[u * 4 + 3] = hpre[t][u].w * a.in_scale;
+          }
+          publish(grp + 2 * t, v, kKC);
+        }
+      } else {
         const float4* fr4 = reinterpret_cast<const float4*>(a.geo + (size_t)cx.g * PP_GEO_STRIDE);
         const float4* pi4 = reinterpret_cast<const float4*>(a.pglob + (size_t)rr * 24);
         const float4* pj4 = reinterpret_cast<const float4*>(a.pglob + (size_t)cx.jrow * 24);
@@ -399,9 +430,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
         if (grp == 0) publish(4, geo, kKC); else publish(5, geo, 8);
       }
       stamp();  // 1: first operand published
+      // next tile's row: resolve it early so that its addresses are ready when the prefetch is issued
+      RowCtx nx = cx;
+      if (it + 1 < niter) nx = row_ctx(it + 1);
 
       // ---- epilogue of G1: x1 = relu(acc + A_i + N_j); the two gathered rows are fetched before the wait
-      {
+      if (!POST) {
         const float* Ai = a.A + (size_t)rr * 128;
         const float* Nj = a.Nn + (size_t)cx.jrow * 128;
         float4 an[2][8];
@@ -430,14 +464,13 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
         }
       }
       stamp();  // 3: x1 published
-      // next tile's row: resolve it and (node path) start fetching its h_E columns now
-      RowCtx nx = cx;
-      if (it + 1 < niter) nx = row_ctx(it + 1);
-      if (!EDGE && it + 1 < niter) load_h(nx, hpre);
+      if (!EDGE && it + 1 < niter) load_h(nx, hpre);  // node message path: start fetching the next tile's h_E now
 
       // ---- epilogue of G2: x2 = relu(acc + b2)
-      mbar_wait(&acc_full[1], accph[1]); accph[1] ^= 1;
-      fence_after_sync();
+      if (!POST) {
+        mbar_wait(&acc_full[1], accph[1]); accph[1] ^= 1;
+        fence_after_sync();
+      }
       stamp();  // 4: G2 complete
       if (!EDGE) {
         // node path: masked sum over the 32 edges of the residue (= the 32 lanes of this warp), layers.py:125-127
@@ -462,20 +495,32 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
           if (r < R) a.out[(size_t)r * 128 + c * 32 + lane] = v[0];
         }
       } else {
+        if (!POST) {
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int c = grp + 2 * t;
-          load_acc(ACC1, c, v);
-          const float* b = prm + kP_B2 + c * 32;
+          for (int t = 0; t < 2; ++t) {
+            const int c = grp + 2 * t;
+            load_acc(ACC1, c, v);
+            const float* b = prm + kP_B2 + c * 32;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + b[i], 0.f);
-          publish(10 + c, v, kKC);
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + b[i], 0.f);
+            publish(10 + c, v, kKC);
+          }
         }
         stamp();  // 5: x2 published
         // ---- epilogue of G3: e = LN2(h_E + mask * (acc + b3))   (layers.py:139-142); e -> TMEM as (hi, lo)
         {
           float4 h[2][8];
-          load_h(cx, h);  // residual; second read of the tile's own rows, L2 resident
+          if (POST) {  // residual = h_V of the residue; b3 enters scaled by the mean attention mask (layers.py:125-128)
+            const float* hv = a.hres + (size_t)rr * 128;
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+#pragma unroll
+              for (int u = 0; u < 8; ++u) h[t][u] = *reinterpret_cast<const float4*>(hv + (grp + 2 * t) * 32 + u * 4);
+          } else {
+            load_h(cx, h);  // residual; second read of the tile's own rows, L2 resident
+          }
+          const float bscale = POST ? a.msum[cx.g] : 1.f;
+          const bool gate = POST ? true : on;
           mbar_wait(&acc_full[0], accph[0]); accph[0] ^= 1;
           fence_after_sync();
           stamp();  // 6: G3 complete
@@ -492,7 +537,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
 #pragma unroll
               for (int q4 = 0; q4 < 4; ++q4) {
                 const int i = u * 4 + q4;
-                x[t][i] = hh[q4] + (on ? v[i] + b[i] : 0.f);
+                x[t][i] = hh[q4] + (gate ? v[i] + b[i] * bscale : 0.f);
                 sum += x[t][i];
               }
             }
@@ -540,7 +585,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
             const float* b = prm + kP_BIN + j * 128 + c * 32;
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + b[i], 0.f);
-            publish(14 + 4 * j + c, v, kKC);
+            publish((POST ? 4 : 14) + 4 * j + c, v, kKC);
           }
           stamp();  // 9 + 2j: hidden slice j published
         }
@@ -569,7 +614,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) { float d = y[t][i] - mean3; var += d * d; }
         const float rstd3 = rsqrtf(row_total(var, 3) * (1.f / 128.f) + 1e-5f);
-        float* orow = a.out + ((size_t)rr * K + (in_range ? k : 0)) * 128;
+        float* orow = POST ? a.out + (size_t)rr * 128 : a.out + ((size_t)rr * K + (in_range ? k : 0)) * 128;
         if (in_range) {
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
@@ -593,7 +638,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
       // end of tile: both accumulators and the FFN operand have been fully read by this thread
       fence_before_sync();
       mbar_arrive(wk_done);
-      qbase += EDGE ? 30 : 10;
+      qbase += POST ? 20 : (EDGE ? 30 : 10);
       cx = nx;
     }  // tile loop
   }
@@ -606,16 +651,16 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
   if (warp == 8) tmem_dealloc<512>(tmem);
 }
 
-template <bool EDGE, int PASSES, int CLUSTER>
+template <int MODE, int PASSES, int CLUSTER>
 static int launch(const Args& a, cudaStream_t stream) {
-  auto kern = edge_tc_kernel<EDGE, PASSES, CLUSTER>;
+  auto kern = edge_tc_kernel<MODE, PASSES, CLUSTER>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTC);
   if (e != cudaSuccess) {
     snprintf(g_last_error, sizeof(g_last_error), "edge_tc_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return 1;
   }
   const long long R = (long long)a.S * a.G;
-  unsigned tiles = (unsigned)((R + 3) / 4);
+  unsigned tiles = (MODE == 2) ? (unsigned)((R + kRows - 1) / kRows) : (unsigned)((R + 3) / 4);
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
@@ -688,11 +733,43 @@ extern "C" int pp_ipmp_edge_tc(const float* weights, int64_t layer, int64_t path
   a.out = out;
   a.trace = g_tc_trace;
   int rc;
-#define PP_TC_CASE(E, P, C) if (path == (E) && passes == (P) && cluster == (C)) rc = tc::launch<(E) != 0, P, C>(a, stream); else
+#define PP_TC_CASE(E, P, C) if (path == (E) && passes == (P) && cluster == (C)) rc = tc::launch<E, P, C>(a, stream); else
   PP_TC_CASE(0, 3, 1) PP_TC_CASE(0, 3, 2) PP_TC_CASE(0, 3, 4) PP_TC_CASE(0, 1, 1) PP_TC_CASE(0, 1, 2) PP_TC_CASE(0, 1, 4)
   PP_TC_CASE(1, 3, 1) PP_TC_CASE(1, 3, 2) PP_TC_CASE(1, 3, 4) PP_TC_CASE(1, 1, 1) PP_TC_CASE(1, 1, 2) PP_TC_CASE(1, 1, 4)
   rc = 2;
-#undef PP_TC_CASE
   if (rc) return rc;
   return check_launch("pp_ipmp_edge_tc");
+}
+
+// Tensor-core version of pp_ipmp_node_post: h_V <- mask * LN1(e + FFN(e)), e = LN0(h_V + W3 mean_k(msg) + b3 mean_k(mask))
+// (reference layers.py:127-132).  wstream = operand images of path 2 of this layer; hV [S*G][128] is updated in place.
+extern "C" int pp_ipmp_node_post_tc(const float* weights, int64_t layer, const float* wstream, const float* msum,
+                                    const float* residue_mask, int64_t G, int64_t K, int64_t S, const float* wsAcc,
+                                    float* hV, int64_t passes, int64_t cluster, cudaStream_t stream) {
+  PP_REQUIRE(weights && wstream && msum && residue_mask && wsAcc && hV, "null pointer");
+  PP_REQUIRE(layer >= 0 && layer < 3, "layer out of range");
+  PP_REQUIRE(G > 0 && S > 0 && K > 0 && K <= PP_KMAX, "bad sizes");
+  PP_REQUIRE(passes == 1 || passes == 3, "passes must be 1 or 3");
+  PP_REQUIRE(cluster == 1 || cluster == 2 || cluster == 4, "cluster must be 1, 2 or 4");
+  const float* Lb = weights + layer * wl::kLayerStride;
+  tc::Args a{};
+  a.G = (int)G; a.K = (int)K; a.S = (int)S;
+  a.wstream = wstream;
+  a.B2 = Lb + PP_OFF(L0_N_B2);
+  a.B3 = Lb + PP_OFF(L0_N_B3);
+  a.LNG = Lb + PP_OFF(L0_LN0_G); a.LNB = Lb + PP_OFF(L0_LN0_B);
+  a.BIN = Lb + PP_OFF(L0_NF_BIN); a.BOUT = Lb + PP_OFF(L0_NF_BOUT);
+  a.LN3G = Lb + PP_OFF(L0_LN1_G); a.LN3B = Lb + PP_OFF(L0_LN1_B);
+  a.hE_in = wsAcc; a.he_shared = 0;
+  a.rmask = residue_mask; a.msum = msum; a.hres = hV;
+  a.in_scale = 1.f / (float)K;
+  a.out = hV;
+  a.trace = nullptr;
+  const int64_t path = 2;
+  int rc;
+  PP_TC_CASE(2, 3, 1) PP_TC_CASE(2, 3, 2) PP_TC_CASE(2, 3, 4) PP_TC_CASE(2, 1, 1) PP_TC_CASE(2, 1, 2) PP_TC_CASE(2, 1, 4)
+  rc = 2;
+#undef PP_TC_CASE
+  if (rc) return rc;
+  return check_launch("pp_ipmp_node_post_tc");
 }

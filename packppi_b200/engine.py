@@ -194,7 +194,12 @@ class Engine:
             else:
                 _lib.call("pp_ipmp_edge_tc", W, layer, 0, self.wtc[layer, 0], *common, G, K, S, hE_in, shared, ws.wsA,
                           ws.wsN, ws.wsP, ws.wsAcc, *tcp, rows=S * G, tag="node")
-            _lib.call("pp_ipmp_node_post", W, layer, *common, graph.msum, *size, ws.wsAcc, ws.hV, rows=S * G)
+            if self.mode == "fp32":
+                _lib.call("pp_ipmp_node_post", W, layer, *common, graph.msum, *size, ws.wsAcc, ws.hV, rows=S * G)
+            else:
+                # per-residue GEMMs are 3 % of the step but h_V feeds everything: always split TF32 here
+                _lib.call("pp_ipmp_node_post_tc", W, layer, self.wtc[layer, 2], graph.msum, graph.mask, G, K, S,
+                          ws.wsAcc, ws.hV, 3, self.cluster, rows=S * G)
             if edge:
                 _lib.call("pp_ipmp_node_pre", W, layer, 1, *common, *size, ws.hV, ws.wsA, ws.wsN, ws.wsP, rows=S * G)
                 if self.mode == "fp32":

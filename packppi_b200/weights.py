@@ -175,18 +175,22 @@ def pack_tc_stream(sd, stream_floats):
       G2: W_inter.0 (4 chunks), G3: W_out (4 chunks)
       FFN slices j = 0..3 (FFN-in = rows 128j..128j+127 of edge_dense.W_in, FFN-out = columns 128j..128j+127 of
       edge_dense.W_out, 4 chunks each), software-pipelined by one slice: in0, in1, out0, in2, out1, in3, out2, out3
-    The node path (path 0) uses G1 and G2 of node_message_fn only; the rest of its stream is zero."""
+    The node path (path 0) uses G1 and G2 of node_message_fn only; the rest of its stream is zero.  Path 2 is the
+    per-residue node epilogue: node_message_fn.W_out (4 chunks) followed by node_dense in the same pipelined order."""
     check_state_dict(sd)
     f = {k: v.detach().to("cpu", torch.float32) for k, v in sd.items()}
-    out = torch.zeros(N_LAYERS, 2, stream_floats, dtype=torch.float32)
+    out = torch.zeros(N_LAYERS, 3, stream_floats, dtype=torch.float32)
     for l in range(N_LAYERS):
         p = f"mpnn.mpnn_layers.{l}."
-        for path, fn in enumerate(("node_message_fn", "edge_message_fn")):
+        for path, fn in enumerate(("node_message_fn", "edge_message_fn", "node_message_fn")):
             Win = f[p + fn + ".W_in.weight"]
             mats = [torch.cat([Win[:, 128:256], Win[:, 416:456]], 1), f[p + fn + ".W_inter.0.weight"]]
-            if path == 1:
+            if path == 2:
+                mats = []
+            if path >= 1:
+                dense = "edge_dense" if path == 1 else "node_dense"
                 mats.append(f[p + fn + ".W_out.weight"])
-                Fi, Fo = f[p + "edge_dense.W_in.weight"], f[p + "edge_dense.W_out.weight"]
+                Fi, Fo = f[p + dense + ".W_in.weight"], f[p + dense + ".W_out.weight"]
                 mats.append(Fi[0:128, :])
                 for j in range(4):
                     if j + 1 < 4:
