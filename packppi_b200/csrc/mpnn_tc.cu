@@ -409,8 +409,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
           for (int u = 0; u < 8; ++u) {
             v[u * 4] = hpre[t][u].x; v[u * 4 + 1] = hpre[t][u].y; v[u * 4 + 2] = hpre[t][u].z; v[u * 4 + 3] = hpre[t][u].w;
           }
+          // edge update: keep the raw row for the residual in the (still unused) FFN-operand region of TMEM instead of
+          // reading it from global memory a second time (a row-per-thread read costs 32 L1 wavefronts per instruction)
+          if (MODE == 1) store_tmem(EH + (grp + 2 * t) * 32, v);
           publish(grp + 2 * t, v, kKC);
         }
+        if (MODE == 1) tmem_st_wait();
         float geo[32];
 #pragma unroll
         for (int pt = 0; pt < 8; ++pt) {
@@ -516,8 +520,6 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
             for (int t = 0; t < 2; ++t)
 #pragma unroll
               for (int u = 0; u < 8; ++u) h[t][u] = *reinterpret_cast<const float4*>(hv + (grp + 2 * t) * 32 + u * 4);
-          } else {
-            load_h(cx, h);  // residual; second read of the tile's own rows, L2 resident
           }
           const float bscale = POST ? a.msum[cx.g] : 1.f;
           const bool gate = POST ? true : on;
@@ -529,17 +531,20 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             const int c = grp + 2 * t;
+            if (POST) {
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                x[t][u * 4] = h[t][u].x; x[t][u * 4 + 1] = h[t][u].y; x[t][u * 4 + 2] = h[t][u].z; x[t][u * 4 + 3] = h[t][u].w;
+              }
+            } else {
+              load_acc(EH, c, x[t]);  // the raw h_E row stashed during the first-operand build
+            }
             load_acc(ACC0, c, v);
             const float* b = prm + kP_B3 + c * 32;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const float hh[4] = {h[t][u].x, h[t][u].y, h[t][u].z, h[t][u].w};
-#pragma unroll
-              for (int q4 = 0; q4 < 4; ++q4) {
-                const int i = u * 4 + q4;
-                x[t][i] = hh[q4] + (gate ? v[i] + b[i] * bscale : 0.f);
-                sum += x[t][i];
-              }
+            for (int i = 0; i < 32; ++i) {
+              x[t][i] += gate ? v[i] + b[i] * bscale : 0.f;
+              sum += x[t][i];
             }
           }
           const float mean = row_total(sum, 0) * (1.f / 128.f);
