@@ -118,9 +118,12 @@ int pp_set_tc_trace(uint64_t* trace);
 /* decoder_score (models/TorsionalDiffusion.py:62-68,106-108) and, if do_step, both SO2VESchedule.step calls in ode
  * mode plus wrap and mask (models/components/schedule.py:198-235, TorsionalDiffusion.py:272-280):
  *   chi <- wrap(chi + [step_mask] c_ode (score * w_anneal)) * chi_mask.
- * score_out [S*G][4] or NULL; step_mask uint8 [G][4]; chi_mask [G][4]; chi [S*G][4] in/out. */
+ * score_out [S*G][4] or NULL; step_mask uint8 [G][4]; chi_mask [G][4]; chi [S*G][4] in/out.
+ * SDE branch (schedule.py:224-228) when noise_1pi / noise_2pi [S*G][4] (the two torch.normal draws of a step) and
+ * mask_1pi uint8 [G][4] are given: chi += c_ode (score * w) + d_sde * noise with c_ode = g^2 dt, d_sde = g sqrt(dt). */
 int pp_decode_step(const float* weights, const float* hV, int64_t G, int64_t S, float* score_out, int64_t do_step,
                    float c_ode, float w_anneal, const uint8_t* step_mask, const float* chi_mask, float* chi,
+                   const float* noise_1pi, const float* noise_2pi, const uint8_t* mask_1pi, float d_sde,
                    pp_stream_t stream);
 
 /* get_atom14_coords (models/components/__init__.py:76-120).  tables [21][pp_table_stride()] from

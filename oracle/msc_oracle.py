@@ -238,6 +238,16 @@ def ode_step(x, score, time, dt, mask, annealed_temp=3):
     return torch.where(mask, new, x)
 
 
+def sde_step(x, score, time, dt, mask, noise, annealed_temp=3):
+    """schedule.py:198-235, sde branch, with the torch.normal draw injected."""
+    sigma = t_to_sigma(time)
+    g = sigma * math.sqrt(2 * math.log(SIGMA_MAX / SIGMA_MIN))
+    alpha = 1 - (sigma / math.exp(math.log(SIGMA_MAX))) ** 2
+    w = annealed_temp / (alpha + (1 - alpha) * annealed_temp)
+    new = x + (g ** 2 * dt * (score * w) + g * torch.sqrt(dt) * noise)
+    return torch.where(mask, new, x)
+
+
 def wrap(x):
     return (x + math.pi) % TWO_PI - math.pi
 
@@ -253,7 +263,7 @@ def initial_noise(batch, eps1, eps2):
     return wrap(x).reshape(B, L, 4)
 
 
-def sampling(sd, batch, SC_D_init, n_steps=30, hoist=True, trajectory=False):
+def sampling(sd, batch, SC_D_init, n_steps=30, hoist=True, trajectory=False, sde_noise=None):
     """TorsionalDiffusion.py:254-283 from an injected initial sample (ODE mode has no other randomness).
 
     hoist=False rebuilds graph and edge embedding every step, as the reference does (CPU-baseline timing).
@@ -271,8 +281,12 @@ def sampling(sd, batch, SC_D_init, n_steps=30, hoist=True, trajectory=False):
             t = time.repeat_interleave(B * L)
             score, _ = network(sd, batch, x, t, cache)
             s = score.reshape(-1, 4)
-            y = ode_step(x.reshape(-1, 4), s, time, dt, m1)
-            y = ode_step(y, s, time, dt, m2)
+            if sde_noise is None:
+                y = ode_step(x.reshape(-1, 4), s, time, dt, m1)
+                y = ode_step(y, s, time, dt, m2)
+            else:  # mode "sde": one normal draw per schedule.step call, [n_steps, 2, B*L, 4]
+                y = sde_step(x.reshape(-1, 4), s, time, dt, m1, sde_noise[j, 0])
+                y = sde_step(y, s, time, dt, m2, sde_noise[j, 1])
             x = wrap(y).reshape(B, L, 4) * batch["SC_D_mask"]
             if trajectory:
                 traj.append(x.clone())

@@ -5,7 +5,10 @@
 // sampling loop (schedule.py:198-235 ode branch, TorsionalDiffusion.py:272-280):
 //     chi <- wrap(chi + [step_mask] * c * (score * w)) * SC_D_mask ,  wrap(x) = (x + pi) mod 2pi - pi
 // with c = 0.5 g(t)^2 dt and w = annealed weight, both evaluated on the host in fp32 exactly as the reference's
-// 0-dim tensor arithmetic does, so the kernel only multiplies.
+// 0-dim tensor arithmetic does, so the kernel only multiplies.  SDE branch (schedule.py:224-228), selected by passing
+// the two noise tensors the reference draws with torch.normal (one per schedule.step call):
+//     chi <- wrap(chi + [step_mask] (c (score * w) + d * noise)) * SC_D_mask,  c = g^2 dt, d = g sqrt(dt),
+// noise = noise_1pi where the chi is pi-periodic, else noise_2pi.
 #include "common.cuh"
 #include "weights_layout.h"
 
@@ -15,7 +18,9 @@ namespace pp {
 __global__ void decode_step_kernel(const float* __restrict__ W, const float* __restrict__ hV, int G, int S,
                                    float* __restrict__ score_out, int do_step, float c_ode, float w_anneal,
                                    const unsigned char* __restrict__ step_mask /*[G][4]*/,
-                                   const float* __restrict__ chi_mask /*[G][4]*/, float* __restrict__ chi /*[R][4]*/) {
+                                   const float* __restrict__ chi_mask /*[G][4]*/, float* __restrict__ chi /*[R][4]*/,
+                                   const float* __restrict__ noise_1pi, const float* __restrict__ noise_2pi /*[R][4]*/,
+                                   const unsigned char* __restrict__ mask_1pi /*[G][4]*/, float d_sde) {
   int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (r >= S * G) return;
@@ -66,7 +71,14 @@ __global__ void decode_step_kernel(const float* __restrict__ W, const float* __r
     if (do_step) {
       int g = r % G;
       float x = chi[o];
-      if (step_mask[(size_t)g * 4 + lane]) x = __fadd_rn(x, __fmul_rn(c_ode, __fmul_rn(a3, w_anneal)));
+      if (step_mask[(size_t)g * 4 + lane]) {
+        float drift = __fmul_rn(c_ode, __fmul_rn(a3, w_anneal));
+        if (noise_1pi) {  // SDE: drift + diffusion, rounded like (drift + diffusion) then x += ...
+          float n = mask_1pi[(size_t)g * 4 + lane] ? noise_1pi[o] : noise_2pi[o];
+          drift = __fadd_rn(drift, __fmul_rn(d_sde, n));
+        }
+        x = __fadd_rn(x, drift);
+      }
       float y = fmodf(__fadd_rn(x, PP_PI_F), PP_TWO_PI_F);
       if (y != 0.f && y < 0.f) y = __fadd_rn(y, PP_TWO_PI_F);  // python-style remainder (torch %)
       chi[o] = __fmul_rn(__fsub_rn(y, PP_PI_F), chi_mask[(size_t)g * 4 + lane]);
@@ -78,13 +90,16 @@ __global__ void decode_step_kernel(const float* __restrict__ W, const float* __r
 
 extern "C" int pp_decode_step(const float* weights, const float* hV, int64_t G, int64_t S, float* score_out,
                               int64_t do_step, float c_ode, float w_anneal, const uint8_t* step_mask,
-                              const float* chi_mask, float* chi, cudaStream_t stream) {
+                              const float* chi_mask, float* chi, const float* noise_1pi, const float* noise_2pi,
+                              const uint8_t* mask_1pi, float d_sde, cudaStream_t stream) {
   PP_REQUIRE(weights && hV, "null pointer");
   PP_REQUIRE(G > 0 && S > 0, "bad sizes");
   PP_REQUIRE(score_out || do_step, "nothing to do");
   PP_REQUIRE(!do_step || (step_mask && chi_mask && chi), "step needs step_mask, chi_mask and chi");
+  PP_REQUIRE(!noise_1pi || (noise_2pi && mask_1pi), "the SDE step needs both noise tensors and the pi-periodic mask");
   long long R = S * G;
   pp::decode_step_kernel<<<(unsigned)((R * 32 + 255) / 256), 256, 0, stream>>>(
-      weights, hV, (int)G, (int)S, score_out, (int)do_step, c_ode, w_anneal, step_mask, chi_mask, chi);
+      weights, hV, (int)G, (int)S, score_out, (int)do_step, c_ode, w_anneal, step_mask, chi_mask, chi, noise_1pi,
+      noise_2pi, mask_1pi, d_sde);
   return pp::check_launch("pp_decode_step");
 }

@@ -216,14 +216,16 @@ class Engine:
         ws = self.workspace(graph.G, graph.K, S)
         ni = self.node_inputs(batch)
         self.forward_layers(graph, ws, ni, chi, t, 1)
-        _lib.call("pp_decode_step", self.wblob, ws.hV, graph.G, S, ws.score, 0, 0.0, 0.0, None, None, None)
+        _lib.call("pp_decode_step", self.wblob, ws.hV, graph.G, S, ws.score, 0, 0.0, 0.0, None, None, None, None, None,
+                  None, 0.0)
         return ws.score, ws.hV
 
     # ------------------------------------------------------------------ sampling
     @staticmethod
-    def ode_coefficients(n_steps=30, annealed_temp=3.0):
-        """Per-step (t, c = 0.5 g^2 dt, w) with the reference's fp32 tensor arithmetic (schedule.py:165-235,286-288,
-        TorsionalDiffusion.py:259-263): the schedule entries are 0-dim fp32 tensors, the numpy scalars fold in."""
+    def ode_coefficients(n_steps=30, annealed_temp=3.0, mode="ode"):
+        """Per-step (t, c, w, d) with the reference's fp32 tensor arithmetic (schedule.py:165-235,286-288,
+        TorsionalDiffusion.py:259-263): the schedule entries are 0-dim fp32 tensors, the numpy scalars fold in.
+        ode: c = 0.5 g^2 dt, d = 0;  sde: c = g^2 dt, d = g sqrt(dt)."""
         sched = torch.linspace(1, 0, n_steps + 1)
         lo, hi = np.log(SIGMA_MIN), np.log(SIGMA_MAX)
         out = []
@@ -236,19 +238,26 @@ class Engine:
                 w = annealed_temp / (alpha + (1 - alpha) * annealed_temp)
             else:
                 w = torch.tensor(1.0)
-            c = 0.5 * g ** 2 * dt
-            out.append((float(time), float(c), float(w)))
+            if mode == "sde":
+                c, d = g ** 2 * dt, g * torch.sqrt(dt)
+            else:
+                c, d = 0.5 * g ** 2 * dt, torch.tensor(0.0)
+            out.append((float(time), float(c), float(w), float(d)))
         return out
 
-    def _run_steps(self, graph, ws, ni, step_mask, chi, tvals, coefs, trajectory=None):
+    def _run_steps(self, graph, ws, ni, step_mask, chi, tvals, coefs, trajectory=None, sde=None):
+        """sde = (mask_1pi uint8 [G,4], noise [steps, 2, S*G, 4]) switches the update to the SDE branch."""
         G, S = graph.G, ws.S
-        for j, (_, c, w) in enumerate(coefs):
+        for j, (_, c, w, d) in enumerate(coefs):
             self.forward_layers(graph, ws, ni, chi, tvals[j:j + 1], 0)
-            _lib.call("pp_decode_step", self.wblob, ws.hV, G, S, None, 1, c, w, step_mask, ni["chi_mask"], chi)
+            n1, n2, m1 = (sde[1][j, 0], sde[1][j, 1], sde[0]) if sde is not None else (None, None, None)
+            _lib.call("pp_decode_step", self.wblob, ws.hV, G, S, None, 1, c, w, step_mask, ni["chi_mask"], chi, n1, n2,
+                      m1, d)
             if trajectory is not None:
                 trajectory.append(chi.clone())
 
-    def sample(self, graph, batch, chi_init, n_steps=30, annealed_temp=3.0, trajectory=None):
+    def sample(self, graph, batch, chi_init, n_steps=30, annealed_temp=3.0, trajectory=None, mode="ode",
+               sde_noise=None, generator=None):
         """Reverse-ODE loop (TorsionalDiffusion.py:259-280) on S samples that share `graph`.
 
         chi_init [S*G,4] on the device; returns the final chi [S*G,4] (a new tensor).  Small problems that come back
@@ -259,7 +268,16 @@ class Engine:
         ni = self.node_inputs(batch)
         step_mask = (batch.chi_1pi_periodic_mask.to(self.dev).reshape(-1, 4).bool() |
                      batch.chi_2pi_periodic_mask.to(self.dev).reshape(-1, 4).bool()).to(torch.uint8).contiguous()
-        coefs = self.ode_coefficients(n_steps, annealed_temp)
+        coefs = self.ode_coefficients(n_steps, annealed_temp, mode)
+        if mode == "sde":  # fresh noise every step: no graph replay; `sde_noise` [steps, 2, S*G, 4] injects the draws
+            if sde_noise is None:
+                sde_noise = torch.randn(n_steps, 2, S * G, 4, device=self.dev, generator=generator)
+            m1 = batch.chi_1pi_periodic_mask.to(self.dev).reshape(-1, 4).to(torch.uint8).contiguous()
+            chi = chi_init.clone().contiguous()
+            tvals = torch.tensor([c[0] for c in coefs], dtype=torch.float32, device=self.dev)
+            self._run_steps(graph, self.workspace(G, K, S), ni, step_mask, chi, tvals, coefs, trajectory,
+                            sde=(m1, sde_noise.to(self.dev, torch.float32).contiguous()))
+            return chi
         key = (S, n_steps, float(annealed_temp), self.mode, self.cluster, id(self))
         small = S * G <= GRAPH_ROWS_MAX and trajectory is None and _lib.PROFILE is None and GRAPH_ROWS_MAX > 0
         if not small or (key not in graph._seen and key not in graph._replay):

@@ -276,12 +276,13 @@ class TDiffusionModule(_PackedModule):
                                   "train with the reference and load its state_dict here")
 
     def sampling(self, batch, use_proximal=False, return_list=False, init_SC_D=None, noise=None, n_samples=None,
-                 generator=None):
+                 generator=None, sde_noise=None):
         """TorsionalDiffusion.py:254-298.  Returns SC_D_sample [B,L,4]; with use_proximal the accepted proximal
         result; with return_list (SC_D_sample, list of 50 [1,L,4] tensors, list of 50 floats).
 
         n_samples = S draws S decoys that share graph and edge embedding and returns [S,B,L,4]
-        (init_SC_D / noise then carry a leading S)."""
+        (init_SC_D / noise then carry a leading S).  With sample_cfg.mode = "sde" (schedule.py:224-228) every step adds
+        g sqrt(dt) * noise; `sde_noise` [steps, 2, S*B*L, 4] injects the two torch.normal draws per step."""
         eng, g = self._graph(batch)
         B, L = g.B, g.L
         S = 1 if n_samples is None else int(n_samples)
@@ -295,9 +296,10 @@ class TDiffusionModule(_PackedModule):
             init_SC_D = torch.stack(inits)
         chi0 = init_SC_D.to(device=dev, dtype=torch.float32).reshape(S * B * L, 4).contiguous()
         smp = self.hparams.sample_cfg
-        if smp.mode != "ode":
-            raise NotImplementedError("only mode='ode' (configs/model/sample_cfg/Sampling.yaml) is implemented")
-        chi = eng.sample(g, batch, chi0, n_steps=len(self.schedule) - 1, annealed_temp=smp.annealed_temp)
+        if smp.mode not in ("ode", "sde"):
+            raise NotImplementedError(f"sample_cfg.mode = {smp.mode!r}: the reference knows 'ode' and 'sde'")
+        chi = eng.sample(g, batch, chi0, n_steps=len(self.schedule) - 1, annealed_temp=smp.annealed_temp,
+                         mode=smp.mode, sde_noise=sde_noise, generator=generator)
         SC_D_sample = chi.reshape(S, B, L, 4) if n_samples is not None else chi.reshape(B, L, 4)
         if not use_proximal:
             return SC_D_sample

@@ -165,6 +165,20 @@ def test_sampling_trajectory(case, model, dev):
     assert abs(m_ref - m_gpu) <= 0.01 * max(m_ref, 1e-6)
 
 
+def test_sde_sampling_with_injected_noise(dev):
+    """sample_cfg.mode = "sde": same trajectory as the reference when its torch.normal draws are injected."""
+    from packppi_b200 import TDiffusionModule, weights
+    g, b = load_golden("1brs_sde")
+    m = TDiffusionModule(sample_cfg=dict(mode="sde"))
+    m.load_state_dict(weights.make_state_dict(0))
+    m = m.to(dev).eval()
+    out = m.sampling(b.to(dev), init_SC_D=tt(g["in_SC_D_init"]).to(dev), sde_noise=tt(g["in_sde_noise"]).to(dev))
+    d = wrapped_diff(out.cpu(), tt(g["ref_SC_D_final"])).max().item()
+    assert d < CHI_TOL, d
+    free = m.sampling(b.to(dev))  # fresh noise from the device generator: finite, wrapped, masked
+    assert torch.isfinite(free).all() and free.abs().max() <= math.pi + 1e-5
+
+
 def _chi_mae(pred, b):
     d = (pred - b.SC_D).abs()
     d = torch.minimum(d, 2 * math.pi - d)

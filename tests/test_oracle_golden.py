@@ -100,3 +100,10 @@ def test_proximal(case):
     np.testing.assert_allclose(np.asarray(losses), g["ref_prox_losses"], rtol=2e-4)
     for i, k in enumerate(g["in_prox_keep"]):
         assert wrapped_diff(snaps[int(k)], tt(g["ref_prox_snaps"][i])).max() < 1e-4
+
+
+def test_sde_sampling_with_injected_noise():
+    """mode "sde" (schedule.py:224-228): the reference's own torch.normal draws are replayed."""
+    g, b = load_golden("1brs_sde")
+    x = mo.sampling(SD, b, tt(g["in_SC_D_init"]), sde_noise=tt(g["in_sde_noise"]))
+    assert wrapped_diff(x, tt(g["ref_SC_D_final"])).max() < 1e-4

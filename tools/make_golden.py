@@ -174,6 +174,35 @@ def main():
     if want("1brs"):
         b = ref_batch_from_protein(ref, pdb.read_pdb(os.path.join(REF_DATA, "1BRS.pdb")))
         run_case(ref, model, "1brs", b, do_prox=50, rows=(0, 57, 120, 194))
+    if want("1brs_sde"):
+        # mode "sde" (schedule.py:224-228): record the torch.normal draws of the reference run so they can be injected
+        b = ref_batch_from_protein(ref, pdb.read_pdb(os.path.join(REF_DATA, "1BRS.pdb")))
+        model.schedule_1pi_periodic.mode = model.schedule_2pi_periodic.mode = "sde"
+        draws, orig_normal = [], torch.normal
+
+        def recording_normal(*a, **k):
+            out = orig_normal(*a, **k)
+            draws.append(out.clone())
+            return out
+
+        torch.manual_seed(1)
+        x_init, _ = model.add_sc_noise(b, torch.ones(b.X.shape[1]))
+        torch.manual_seed(1)
+        torch.normal = recording_normal
+        try:
+            with torch.no_grad():
+                x_final = model.sampling(b, use_proximal=False)
+        finally:
+            torch.normal = orig_normal
+            model.schedule_1pi_periodic.mode = model.schedule_2pi_periodic.mode = "ode"
+        assert len(draws) == 60
+        gd = {}
+        save_inputs(gd, b)
+        gd["in_SC_D_init"] = x_init.numpy()
+        gd["in_sde_noise"] = torch.stack(draws).reshape(30, 2, -1, 4).numpy()
+        gd["ref_SC_D_final"] = x_final.numpy()
+        np.savez_compressed(os.path.join(OUT, "1brs_sde.npz"), **gd)
+        print("1brs_sde written", flush=True)
     if want("t1124"):
         b = ref_batch_from_protein(ref, pdb.read_pdb(os.path.join(REF_DATA, "T1124_lig.pdb")))
         run_case(ref, model, "t1124", b, do_prox=0, traj_steps=[0, 1, 9, 19, 29], rows=(100, 619, 620),
