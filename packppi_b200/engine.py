@@ -194,10 +194,13 @@ class Engine:
             else:
                 _lib.call("pp_ipmp_edge_tc", W, layer, 0, self.wtc[layer, 0], *common, G, K, S, hE_in, shared, ws.wsA,
                           ws.wsN, ws.wsP, ws.wsAcc, *tcp, rows=S * G, tag="node")
-            if self.mode == "fp32":
+            if self.mode != "tf32":
+                # h_V feeds every later GEMM of the step: measured on the fixtures, running this per-residue epilogue
+                # in split TF32 raises the 30-step chi error from 1.9e-5 to 7e-5 rad (gate 1e-4) for 3 % of speed,
+                # so the parity modes keep it on the exact-fp32 FFMA kernel
                 _lib.call("pp_ipmp_node_post", W, layer, *common, graph.msum, *size, ws.wsAcc, ws.hV, rows=S * G)
             else:
-                # per-residue GEMMs are 3 % of the step but h_V feeds everything: always split TF32 here
+                # fast mode: tensor cores, but split TF32 even here (plain TF32 would triple the chi error)
                 _lib.call("pp_ipmp_node_post_tc", W, layer, self.wtc[layer, 2], graph.msum, graph.mask, G, K, S,
                           ws.wsAcc, ws.hV, 3, self.cluster, rows=S * G)
             if edge:

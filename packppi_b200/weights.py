@@ -154,7 +154,8 @@ def pack_weights(sd, layout, total_floats):
 
 
 def _tf32_split(w):
-    """w = hi + lo exactly, hi representable in TF32 (low 13 mantissa bits cleared)."""
+    """w = hi + lo exactly, hi = w truncated to TF32 (low 13 mantissa bits cleared), lo left unrounded; same split as
+    split_tf32 in csrc/umma.cuh (truncation measured more accurate end to end than round-to-nearest)."""
     hi = (w.contiguous().view(torch.int32) & -8192).view(torch.float32)
     return hi, w - hi
 
