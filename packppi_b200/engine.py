@@ -141,6 +141,7 @@ class Engine:
         self.wtc = pack_tc_stream(state_dict, _lib.load().pp_tc_stream_floats()).to(self.dev)
         self.tables = DeviceTables.get(self.dev)
         self._ws = {}
+        self._sched = {}
 
     # ------------------------------------------------------------------ graph
     def build_graph(self, batch, with_edges=True, reuse=None):
@@ -248,6 +249,14 @@ class Engine:
             out.append((float(time), float(c), float(w), float(d)))
         return out
 
+    def _schedule(self, n_steps, annealed_temp, mode):
+        """(coefficients, device tensor of the step times), cached: building them costs a host->device copy."""
+        key = (n_steps, float(annealed_temp), mode)
+        if key not in self._sched:
+            coefs = self.ode_coefficients(n_steps, annealed_temp, mode)
+            self._sched[key] = (coefs, torch.tensor([c[0] for c in coefs], dtype=torch.float32, device=self.dev))
+        return self._sched[key]
+
     def _run_steps(self, graph, ws, ni, step_mask, chi, tvals, coefs, trajectory=None, sde=None):
         """sde = (mask_1pi uint8 [G,4], noise [steps, 2, S*G, 4]) switches the update to the SDE branch."""
         G, S = graph.G, ws.S
@@ -271,13 +280,12 @@ class Engine:
         ni = self.node_inputs(batch)
         step_mask = (batch.chi_1pi_periodic_mask.to(self.dev).reshape(-1, 4).bool() |
                      batch.chi_2pi_periodic_mask.to(self.dev).reshape(-1, 4).bool()).to(torch.uint8).contiguous()
-        coefs = self.ode_coefficients(n_steps, annealed_temp, mode)
+        coefs, tvals = self._schedule(n_steps, annealed_temp, mode)
         if mode == "sde":  # fresh noise every step: no graph replay; `sde_noise` [steps, 2, S*G, 4] injects the draws
             if sde_noise is None:
                 sde_noise = torch.randn(n_steps, 2, S * G, 4, device=self.dev, generator=generator)
             m1 = batch.chi_1pi_periodic_mask.to(self.dev).reshape(-1, 4).to(torch.uint8).contiguous()
             chi = chi_init.clone().contiguous()
-            tvals = torch.tensor([c[0] for c in coefs], dtype=torch.float32, device=self.dev)
             self._run_steps(graph, self.workspace(G, K, S), ni, step_mask, chi, tvals, coefs, trajectory,
                             sde=(m1, sde_noise.to(self.dev, torch.float32).contiguous()))
             return chi
@@ -286,14 +294,12 @@ class Engine:
         if not small or (key not in graph._seen and key not in graph._replay):
             graph._seen.add(key)
             chi = chi_init.clone().contiguous()
-            tvals = torch.tensor([c[0] for c in coefs], dtype=torch.float32, device=self.dev)
             self._run_steps(graph, self.workspace(G, K, S), ni, step_mask, chi, tvals, coefs, trajectory)
             return chi
         st = graph._replay.get(key)
         if st is None:  # second call with these buffers: capture
             st = dict(ws=Workspace(G, K, S, self.dev), chi=chi_init.clone().contiguous(),
-                      ni={k: v.clone() for k, v in ni.items()}, step_mask=step_mask.clone(),
-                      tvals=torch.tensor([c[0] for c in coefs], dtype=torch.float32, device=self.dev))
+                      ni={k: v.clone() for k, v in ni.items()}, step_mask=step_mask.clone(), tvals=tvals)
             torch.cuda.synchronize(self.dev)
             cg = torch.cuda.CUDAGraph()
             with torch.cuda.graph(cg):

@@ -85,12 +85,16 @@ def test_ode_coefficients_closed_form():
     from packppi_b200.engine import Engine
     co = Engine.ode_coefficients(30, 3)
     assert len(co) == 30 and abs(co[0][0] - 1.0) < 1e-7
-    for t, c, w in co:
+    for t, c, w, d in co:
         sigma = np.exp(np.log(0.01 * np.pi) + np.log(100.0) * t)
         g2 = sigma ** 2 * 2 * np.log(100.0)
         alpha = 1 - (sigma / np.pi) ** 2
-        assert abs(c - 0.5 * g2 / 30) < 1e-5 * max(1.0, c)
+        assert abs(c - 0.5 * g2 / 30) < 1e-5 * max(1.0, c) and d == 0.0
         assert abs(w - 3 / (alpha + 3 * (1 - alpha))) < 1e-5
+    # SDE branch (schedule.py:224-228): c = g^2 dt, d = g sqrt(dt)
+    for (t, c, w, d), (_, c_ode, w_ode, _) in zip(Engine.ode_coefficients(30, 3, mode="sde"), co):
+        assert abs(c - 2 * c_ode) < 1e-5 * max(1.0, c) and w == w_ode
+        assert abs(d * d - c) < 1e-5 * max(1.0, c)
 
 
 def test_dist_bounds_and_reach():
