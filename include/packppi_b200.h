@@ -187,6 +187,10 @@ int pp_prox_init_from_mean(const float* per_res, const float* mean, const float*
  * Pins the descriptor encodings the fused tensor-core kernels rely on (tests/test_gpu_umma.py). */
 int pp_selftest_umma(const float* A, const float* W, float* D, int64_t K, int64_t passes, int64_t ts_mode,
                      pp_stream_t stream);
+/* Same tile through kind::f16 with fp16 (hi, lo) operand pairs (the format the fused kernels use): passes 1 = plain
+ * fp16 inputs, 3 = split fp16 (~fp32).  ts_mode != 0 feeds A from tensor memory as packed fp16 pairs. */
+int pp_selftest_umma_f16(const float* A, const float* W, float* D, int64_t K, int64_t passes, int64_t ts_mode,
+                         pp_stream_t stream);
 
 #ifdef __cplusplus
 }

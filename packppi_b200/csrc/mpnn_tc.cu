@@ -8,17 +8,20 @@
 //              four 32-column chunks.  They build the first A operand, then act as the epilogue of every GEMM:
 //              tcgen05.ld 32 columns -> bias / ReLU / LayerNorm -> next A operand, written into a shared-memory ring
 //              (or into TMEM for the FFN input); gathered rows are fetched before the wait on the accumulator
-//   warp 8     MMA issuer (one elected lane): tcgen05.mma kind::tf32, accumulators ping-pong between two 128-column
-//              TMEM regions, completion signalled with tcgen05.commit on mbarriers
+//   warp 8     MMA issuer (one elected lane): tcgen05.mma kind::f16 (K = 16 per instruction), accumulators ping-pong
+//              between two 128-column TMEM regions, completion signalled with tcgen05.commit on mbarriers
 //   warp 9     weight loader: cp.async.bulk of pre-packed operand images (K-major core-matrix layout, consumption
 //              order, see pack_tc_stream in packppi_b200/weights.py) into a ring; with CLUSTER > 1 every CTA fetches
 //              1/CLUSTER of each image and multicasts it to the whole cluster, dividing the L2 -> SM weight traffic
 // A chunks are consumed by the MMA warp as soon as they are written, so the epilogue of GEMM n overlaps the MMAs of
-// GEMM n+1.  The FFN input e = LayerNorm(...) is kept in TMEM as (hi, lo) and fed to the four 128-wide slices of
-// the 128 -> 512 Linear as a TMEM A operand; hi + lo is e exactly, so it also serves as the residual.
+// GEMM n+1.  The FFN input e = LayerNorm(...) is kept in TMEM twice: as packed fp16 (hi, lo) pairs, the TMEM A
+// operand of the four 128-wide slices of the 128 -> 512 Linear, and in fp32 for the residual.
 //
-// Precision (PASSES): 3 = split TF32, x = hi + lo with hi = x truncated to TF32: hi*hi + hi*lo + lo*hi keeps 21+
-// mantissa bits per product with fp32 accumulation (parity mode); 1 = plain TF32 (fast mode, looser tolerance).
+// Precision (PASSES): 3 = split fp16, x ~= hi + lo with both halves rounded to nearest fp16: hi*hi + hi*lo + lo*hi
+// keeps 22 mantissa bits per product with fp32 accumulation (parity mode) and runs on kind::f16, twice the rate of
+// kind::tf32; 1 = hi only (11 bits, the precision of TF32; fast mode, looser tolerance).  Weight images are
+// pre-scaled by a power of two per matrix (weights.py: pack_tc_stream) so that their lo halves stay in the normal
+// fp16 range; the epilogues multiply the accumulator by the inverse scale (exact).
 #include "common.cuh"
 #include "umma.cuh"
 #include "weights_layout.h"
@@ -30,34 +33,32 @@ using namespace umma;
 
 constexpr int kRows = 128;
 constexpr int kKC = 32;
-constexpr int kSA = 3;   // A ring: slots of 32 k-columns (hi + lo images, 32 KB)
-constexpr int kSB = 6;   // B ring: sub-slots of 16 k-columns (hi + lo images, 16 KB)
-constexpr int kImgFloats = kRows * kKC;          // one operand image (hi or lo) of a 32-column chunk
-constexpr uint32_t kImgBytes = kImgFloats * 4;   // 16 KB
-constexpr int kSlotFloats = 2 * kImgFloats;      // hi + lo
-constexpr int kSubK = 16;                        // k-columns per B sub-slot
-constexpr int kSubImgFloats = kRows * kSubK;     // 8 KB image
-constexpr int kSubFloats = 2 * kSubImgFloats;
+constexpr int kSA = 6;   // A ring: slots of 32 k-columns (fp16 hi + lo images, 16 KB)
+constexpr int kSB = 6;   // B ring: slots of one weight chunk (<= 32 k-columns, hi + lo images, 16 KB)
+constexpr uint32_t kImgBytes = kRows * kKC * 2;  // one fp16 operand image (hi or lo) of a 32-column chunk: 8 KB
+constexpr uint32_t kSlotBytes = 2 * kImgBytes;   // hi + lo
 constexpr int kThreadsTC = 320;  // 8 worker warps (two groups of 128 rows), MMA warp, loader warp
 constexpr uint32_t kLbo = kRows * 16, kSbo = 128;
-constexpr uint32_t kIdesc = idesc_tf32(128, 128);
+constexpr uint32_t kIdesc = idesc_f16(128, 128);
+constexpr int kPairKC = 16;                      // last G1 chunk: 8 pair distances padded to one K = 16 instruction
 
-constexpr int kChunksNode = 10;                  // G1 (5x32 + 8), G2 (4x32)
+constexpr int kChunksNode = 10;                  // G1 (5x32 + 16), G2 (4x32)
 constexpr int kChunksEdge = 6 + 4 + 4 + 4 * 8;   // + G3, 4 x (FFN-in slice, FFN-out slice)
-constexpr long long kStreamFloats = 2LL * 128 * (168 + 128 + 128 + 4 * 256);
+// operand images (fp16 hi + lo) of one layer / path, followed by 8 floats: 1 / scale of G1, G2, G3, FFN-in, FFN-out
+constexpr long long kImageFloats = 2LL * 128 * (176 + 128 + 128 + 4 * 256) * 2 / 4;
+constexpr long long kStreamFloats = kImageFloats + 8;
 
 constexpr size_t kBarBytes = (2 * kSA + 2 * kSB + 2 + 1) * 8;
 // per-column parameters staged in shared memory (floats): b2, b3, LN2 gain/bias, FFN b_in (512), b_out, LN3 gain/bias
 constexpr int kP_B2 = 0, kP_B3 = 128, kP_LN2G = 256, kP_LN2B = 384, kP_BIN = 512, kP_BOUT = 1024, kP_LN3G = 1152,
               kP_LN3B = 1280, kParamFloats = 1408;
 constexpr int kRedFloats = 4 * 2 * 128;  // four row reductions x two groups
-constexpr size_t kSmemTC = ((size_t)kSA * kSlotFloats + (size_t)kSB * kSubFloats) * 4 + kBarBytes + 16 +
-                           (kParamFloats + kRedFloats) * 4;
+constexpr size_t kSmemTC = ((size_t)kSA + kSB) * kSlotBytes + kBarBytes + 16 + (kParamFloats + kRedFloats) * 4;
 
 struct Args {
   const float* geo; const int* nbr; const float* matt;
   int G, K, S;
-  const float* wstream;   // operand images of this layer / path
+  const float* wstream;   // operand images of this layer / path, then the inverse scales
   const float *B2, *B3, *LNG, *LNB, *BIN, *BOUT, *LN3G, *LN3B;
   const float* hE_in; int he_shared;
   const float *A, *Nn, *pglob;
@@ -95,20 +96,19 @@ __device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
       : "memory");
 }
 
-// write this thread's row of a chunk (kc columns, v[0..kc)) into an A ring slot in the UMMA core-matrix layout
+// write this thread's row of a chunk (kc columns, v[0..kc)) into an A ring slot in the UMMA core-matrix layout:
+// 8 fp16 values = one 16-byte core-matrix row; the 32 lanes of a warp write 512 contiguous bytes (conflict-free)
 template <int PASSES>
-__device__ __forceinline__ void put_chunk(float* slot, int m, const float* v, int kc) {
-  float* hi = slot;
-  float* lo = slot + kImgFloats;
-  const int base = (m >> 3) * 32 + (m & 7) * 4;
+__device__ __forceinline__ void put_chunk(uint8_t* slot, int m, const float* v, int kc) {
+  const int base = (m >> 3) * 128 + (m & 7) * 16;
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    if (u * 4 < kc) {
-      float4 h, l;
-      split_tf32(v[u * 4 + 0], h.x, l.x); split_tf32(v[u * 4 + 1], h.y, l.y);
-      split_tf32(v[u * 4 + 2], h.z, l.z); split_tf32(v[u * 4 + 3], h.w, l.w);
-      *reinterpret_cast<float4*>(hi + u * (kRows * 4) + base) = h;
-      if (PASSES == 3) *reinterpret_cast<float4*>(lo + u * (kRows * 4) + base) = l;
+  for (int u = 0; u < 4; ++u) {
+    if (u * 8 < kc) {
+      uint4 h, l;
+      split_f16x2(v[u * 8 + 0], v[u * 8 + 1], h.x, l.x); split_f16x2(v[u * 8 + 2], v[u * 8 + 3], h.y, l.y);
+      split_f16x2(v[u * 8 + 4], v[u * 8 + 5], h.z, l.z); split_f16x2(v[u * 8 + 6], v[u * 8 + 7], h.w, l.w);
+      *reinterpret_cast<uint4*>(slot + u * kLbo + base) = h;
+      if (PASSES == 3) *reinterpret_cast<uint4*>(slot + kImgBytes + u * kLbo + base) = l;
     }
   }
 }
@@ -130,9 +130,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
   constexpr bool EDGE = MODE != 0;   // runs the G3 / LayerNorm / FFN part
   constexpr bool POST = MODE == 2;   // per-residue rows instead of per-edge rows, no G1 / G2
   extern __shared__ __align__(1024) uint8_t smem[];
-  float* Aring = reinterpret_cast<float*>(smem);
-  float* Bring = Aring + kSA * kSlotFloats;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Bring + kSB * kSubFloats);
+  uint8_t* Aring = smem;
+  uint8_t* Bring = Aring + kSA * kSlotBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Bring + kSB * kSlotBytes);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kSA;
   uint64_t* b_full = a_empty + kSA;
@@ -172,7 +172,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
   if (CLUSTER > 1) cluster_sync_all();  // every CTA's barriers exist before any remote arrive / multicast
   fence_after_sync();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t ACC0 = tmem, ACC1 = tmem + 128, EH = tmem + 256, EL = tmem + 384;
+  // TMEM columns: two accumulators, e in fp32 (residual; before that the raw h_E row), e as packed fp16 hi / lo
+  const uint32_t ACC0 = tmem, ACC1 = tmem + 128, E32 = tmem + 256, EH = tmem + 384, EL = tmem + 448;
 
   if (warp == 9) {
     // ------------------------------------------------------------------ weight loader
@@ -180,29 +181,23 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
       Ring rb_{0, 1};
       const uint32_t crank = (CLUSTER > 1) ? cluster_rank() : 0;
       for (int it = 0; it < niter; ++it) {
-        const float* src = a.wstream;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wstream);
         constexpr int NCHUNK = POST ? 36 : (EDGE ? kChunksEdge : kChunksNode);
         for (int i = 0; i < NCHUNK; ++i) {
-          const int kc = (!POST && i == 5) ? 8 : kKC;
-          for (int h = 0; h * kSubK < kc; ++h) {
-            const int kcs = min(kSubK, kc - h * kSubK);
-            const uint32_t img = (uint32_t)kRows * kcs * 4;
-            const float* shi = src + h * kSubImgFloats;
-            const float* slo = src + kRows * kc + h * kSubImgFloats;
-            mbar_wait(&b_empty[rb_.idx], rb_.phase);
-            mbar_arrive_expect_tx(&b_full[rb_.idx], img * (PASSES == 3 ? 2 : 1));
-            float* dst = Bring + rb_.idx * kSubFloats;
-            if (CLUSTER == 1) {
-              bulk_g2s(dst, shi, img, &b_full[rb_.idx]);
-              if (PASSES == 3) bulk_g2s(dst + kSubImgFloats, slo, img, &b_full[rb_.idx]);
-            } else {
-              const uint32_t piece = img / CLUSTER, po = crank * piece / 4;
-              bulk_g2s_mc(dst + po, shi + po, piece, &b_full[rb_.idx], kMask);
-              if (PASSES == 3) bulk_g2s_mc(dst + kSubImgFloats + po, slo + po, piece, &b_full[rb_.idx], kMask);
-            }
-            rb_.next(kSB);
+          const int kc = (!POST && i == 5) ? kPairKC : kKC;
+          const uint32_t img = (uint32_t)kRows * kc * 2;          // hi image; the lo image follows it in the stream
+          const uint32_t bytes = img * (PASSES == 3 ? 2 : 1);
+          mbar_wait(&b_empty[rb_.idx], rb_.phase);
+          mbar_arrive_expect_tx(&b_full[rb_.idx], bytes);
+          uint8_t* dst = Bring + rb_.idx * kSlotBytes;
+          if (CLUSTER == 1) {
+            bulk_g2s(dst, src, bytes, &b_full[rb_.idx]);
+          } else {
+            const uint32_t piece = bytes / CLUSTER, po = crank * piece;
+            bulk_g2s_mc(dst + po, src + po, piece, &b_full[rb_.idx], kMask);
           }
-          src += 2 * kRows * kc;
+          rb_.next(kSB);
+          src += 2 * img;
         }
       }
     }
@@ -212,32 +207,31 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
       Ring ra{0, 0}, rbq{0, 0};
       uint32_t wk_phase = 0;
       auto chunk = [&](bool ss, uint32_t acc, uint32_t a_col, int kc, bool fresh) {
+        // pass 0: hi * hi, pass 1: hi * lo, pass 2: lo * hi; a_col = first packed TMEM column of a TS chunk
         if (ss) mbar_wait(&a_full[ra.idx], ra.phase);
-        const uint32_t as = smem_u32(Aring + ra.idx * kSlotFloats);
-        for (int h = 0; h * kSubK < kc; ++h) {
-          const int kcs = min(kSubK, kc - h * kSubK);
-          mbar_wait(&b_full[rbq.idx], rbq.phase);
-          fence_after_sync();
-          const uint32_t bs = smem_u32(Bring + rbq.idx * kSubFloats);
+        const uint32_t as = smem_u32(Aring + ra.idx * kSlotBytes);
+        mbar_wait(&b_full[rbq.idx], rbq.phase);
+        fence_after_sync();
+        const uint32_t bs = smem_u32(Bring + rbq.idx * kSlotBytes);
+        const uint32_t blo = (uint32_t)kRows * kc * 2;
 #pragma unroll
-          for (int p = 0; p < PASSES; ++p) {
-            const uint32_t ao = (p == 2) ? kImgBytes : 0, bo = (p == 1) ? (uint32_t)kSubImgFloats * 4 : 0;
-            for (int kk = 0; kk < kcs; kk += 8) {
-              const uint64_t bd = smem_desc(bs + bo + (kk / 4) * kLbo, kLbo, kSbo);
-              const uint32_t accum = (fresh && h == 0 && p == 0 && kk == 0) ? 0u : 1u;
-              if (ss) mma_tf32_ss(acc, smem_desc(as + ao + (h * 4 + kk / 4) * kLbo, kLbo, kSbo), bd, kIdesc, accum);
-              else mma_tf32_ts(acc, ((p == 2) ? EL : EH) + a_col + h * kSubK + kk, bd, kIdesc, accum);
-            }
+        for (int p = 0; p < PASSES; ++p) {
+          const uint32_t ao = (p == 2) ? kImgBytes : 0, bo = (p == 1) ? blo : 0;
+          for (int kk = 0; kk < kc; kk += 16) {
+            const uint64_t bd = smem_desc(bs + bo + (kk / 8) * kLbo, kLbo, kSbo);
+            const uint32_t accum = (fresh && p == 0 && kk == 0) ? 0u : 1u;
+            if (ss) mma_f16_ss(acc, smem_desc(as + ao + (kk / 8) * kLbo, kLbo, kSbo), bd, kIdesc, accum);
+            else mma_f16_ts(acc, ((p == 2) ? EL : EH) + a_col + kk / 2, bd, kIdesc, accum);
           }
-          if (CLUSTER == 1) mma_commit(&b_empty[rbq.idx]); else mma_commit_mc(&b_empty[rbq.idx], kMask);
-          rbq.next(kSB);
         }
+        if (CLUSTER == 1) mma_commit(&b_empty[rbq.idx]); else mma_commit_mc(&b_empty[rbq.idx], kMask);
+        rbq.next(kSB);
         if (ss) { mma_commit(&a_empty[ra.idx]); ra.next(kSA); }
       };
       for (int it = 0; it < niter; ++it) {
         if (!POST) {
           // G1: [h_E | pair] (168) -> ACC0
-          for (int c = 0; c < 6; ++c) chunk(true, ACC0, 0, c == 5 ? 8 : kKC, c == 0);
+          for (int c = 0; c < 6; ++c) chunk(true, ACC0, 0, c == 5 ? kPairKC : kKC, c == 0);
           mma_commit(&acc_full[0]);
           // G2 -> ACC1
           for (int c = 0; c < 4; ++c) chunk(true, ACC1, 0, kKC, c == 0);
@@ -252,14 +246,14 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
           mbar_wait(wk_done, wk_phase);  // e is in TMEM, ACC0 / ACC1 are drained
           wk_phase ^= 1;
           fence_after_sync();
-          for (int c = 0; c < 4; ++c) chunk(false, ACC1, c * kKC, kKC, c == 0);  // FFN-in slice 0: A = e from TMEM
+          for (int c = 0; c < 4; ++c) chunk(false, ACC1, c * (kKC / 2), kKC, c == 0);  // FFN-in slice 0: A = e from TMEM
           mma_commit(&acc_full[1]);
           for (int j = 0; j < 4; ++j) {
             if (j + 1 < 4) {
               mbar_wait(wk_done, wk_phase);  // slice j has been read out of ACC1 (and published)
               wk_phase ^= 1;
               fence_after_sync();
-              for (int c = 0; c < 4; ++c) chunk(false, ACC1, c * kKC, kKC, c == 0);  // FFN-in slice j+1
+              for (int c = 0; c < 4; ++c) chunk(false, ACC1, c * (kKC / 2), kKC, c == 0);  // FFN-in slice j+1
               mma_commit(&acc_full[1]);
             }
             for (int c = 0; c < 4; ++c) chunk(true, ACC0, 0, kKC, j == 0 && c == 0);  // FFN-out slice j accumulates
@@ -279,6 +273,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
     const int grp = tid >> 7, m = tid & 127, rl = m >> 5, k = lane;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t accph[2] = {0, 0};
+    const float* wsc = a.wstream + kImageFloats;  // 1 / scale of the weight images
+    const float sG1 = wsc[0], sG2 = wsc[1], sG3 = wsc[2], sFI = wsc[3], sFO = wsc[4];
     int qbase = 0;  // running A-chunk counter (ring position persists across tiles)
 
     struct RowCtx {  // where this thread's edge row of a tile lives
@@ -350,7 +346,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
         const int q = qbase + qrel;
         const int slot = q % kSA;
         mbar_wait(&a_empty[slot], ((q / kSA) & 1) ^ 1);
-        put_chunk<PASSES>(Aring + slot * kSlotFloats, m, vals, kc);
+        put_chunk<PASSES>(Aring + slot * kSlotBytes, m, vals, kc);
         fence_async_smem();
         mbar_arrive(&a_full[slot]);
       };
@@ -411,11 +407,13 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
           }
           // edge update: keep the raw row for the residual in the (still unused) FFN-operand region of TMEM instead of
           // reading it from global memory a second time (a row-per-thread read costs 32 L1 wavefronts per instruction)
-          if (MODE == 1) store_tmem(EH + (grp + 2 * t) * 32, v);
+          if (MODE == 1) store_tmem(E32 + (grp + 2 * t) * 32, v);
           publish(grp + 2 * t, v, kKC);
         }
         if (MODE == 1) tmem_st_wait();
         float geo[32];
+#pragma unroll
+        for (int i = 8; i < kPairKC; ++i) geo[i] = 0.f;  // zero padding of the distance chunk (group 1)
 #pragma unroll
         for (int pt = 0; pt < 8; ++pt) {
           const float jx = pj[pt * 3], jy = pj[pt * 3 + 1], jz = pj[pt * 3 + 2];
@@ -431,7 +429,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
             geo[pt] = sqrtf(gx * gx + gy * gy + gz * gz + 1e-8f);
           }
         }
-        if (grp == 0) publish(4, geo, kKC); else publish(5, geo, 8);
+        if (grp == 0) publish(4, geo, kKC); else publish(5, geo, kPairKC);
       }
       stamp();  // 1: first operand published
       // next tile's row: resolve it early so that its addresses are ready when the prefetch is issued
@@ -459,10 +457,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
           load_acc(ACC0, grp + 2 * t, v);
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            v[u * 4 + 0] = fmaxf(v[u * 4 + 0] + an[t][u].x, 0.f);
-            v[u * 4 + 1] = fmaxf(v[u * 4 + 1] + an[t][u].y, 0.f);
-            v[u * 4 + 2] = fmaxf(v[u * 4 + 2] + an[t][u].z, 0.f);
-            v[u * 4 + 3] = fmaxf(v[u * 4 + 3] + an[t][u].w, 0.f);
+            v[u * 4 + 0] = fmaxf(fmaf(v[u * 4 + 0], sG1, an[t][u].x), 0.f);
+            v[u * 4 + 1] = fmaxf(fmaf(v[u * 4 + 1], sG1, an[t][u].y), 0.f);
+            v[u * 4 + 2] = fmaxf(fmaf(v[u * 4 + 2], sG1, an[t][u].z), 0.f);
+            v[u * 4 + 3] = fmaxf(fmaf(v[u * 4 + 3], sG1, an[t][u].w), 0.f);
           }
           publish(6 + grp + 2 * t, v, kKC);
         }
@@ -484,7 +482,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
           load_acc(ACC1, c, v);
           const float* b = prm + kP_B2 + c * 32;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = on ? fmaxf(v[i] + b[i], 0.f) : 0.f;
+          for (int i = 0; i < 32; ++i) v[i] = on ? fmaxf(fmaf(v[i], sG2, b[i]), 0.f) : 0.f;
           // transpose-reduce: after the 5 steps lane l holds the sum of column l over the 32 lanes
 #pragma unroll
           for (int step = 16; step >= 1; step >>= 1) {
@@ -506,7 +504,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
             load_acc(ACC1, c, v);
             const float* b = prm + kP_B2 + c * 32;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + b[i], 0.f);
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(fmaf(v[i], sG2, b[i]), 0.f);
             publish(10 + c, v, kKC);
           }
         }
@@ -537,13 +535,13 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
                 x[t][u * 4] = h[t][u].x; x[t][u * 4 + 1] = h[t][u].y; x[t][u * 4 + 2] = h[t][u].z; x[t][u * 4 + 3] = h[t][u].w;
               }
             } else {
-              load_acc(EH, c, x[t]);  // the raw h_E row stashed during the first-operand build
+              load_acc(E32, c, x[t]);  // the raw h_E row stashed during the first-operand build
             }
             load_acc(ACC0, c, v);
             const float* b = prm + kP_B3 + c * 32;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              x[t][i] += gate ? v[i] + b[i] * bscale : 0.f;
+              x[t][i] += gate ? fmaf(v[i], sG3, b[i] * bscale) : 0.f;
               sum += x[t][i];
             }
           }
@@ -559,14 +557,14 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
             const int c = grp + 2 * t;
             const float* gm = prm + kP_LN2G + c * 32;
             const float* bt = prm + kP_LN2B + c * 32;
-            float lo[32];
+            uint32_t eh[16], el[16];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float e = (x[t][i] - mean) * rstd * gm[i] + bt[i];
-              split_tf32(e, v[i], lo[i]);
-            }
-            store_tmem(EH + c * 32, v);
-            store_tmem(EL + c * 32, lo);
+            for (int i = 0; i < 32; ++i) v[i] = (x[t][i] - mean) * rstd * gm[i] + bt[i];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) split_f16x2(v[2 * i], v[2 * i + 1], eh[i], el[i]);
+            store_tmem(E32 + c * 32, v);
+            tmem_st16(EH + lane_base + c * 16, eh);
+            if (PASSES == 3) tmem_st16(EL + lane_base + c * 16, el);
           }
           tmem_st_wait();
           fence_before_sync();
@@ -589,7 +587,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
             }
             const float* b = prm + kP_BIN + j * 128 + c * 32;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + b[i], 0.f);
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(fmaf(v[i], sFI, b[i]), 0.f);
             publish((POST ? 4 : 14) + 4 * j + c, v, kKC);
           }
           stamp();  // 9 + 2j: hidden slice j published
@@ -603,14 +601,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           const int c = grp + 2 * t;
-          load_acc(EH, c, y[t]);
-          load_acc(EL, c, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) y[t][i] += v[i];
+          load_acc(E32, c, y[t]);
           load_acc(ACC0, c, v);
           const float* b = prm + kP_BOUT + c * 32;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) { y[t][i] += v[i] + b[i]; sum += y[t][i]; }
+          for (int i = 0; i < 32; ++i) { y[t][i] += fmaf(v[i], sFO, b[i]); sum += y[t][i]; }
         }
         const float mean3 = row_total(sum, 2) * (1.f / 128.f);
         float var = 0.f;
@@ -712,7 +707,7 @@ extern "C" int pp_set_tc_trace(uint64_t* trace) {
 
 // Tensor-core version of pp_ipmp_edge_node (path = 0) and pp_ipmp_edge_edge (path = 1).
 //   wstream: operand images of this layer and path, pp_tc_stream_floats() floats (weights.py: pack_tc_stream)
-//   passes : 3 = split TF32 (fp32-grade), 1 = plain TF32;  cluster: 1, 2 or 4 CTAs sharing the weight stream
+//   passes : 3 = split fp16 (fp32-grade), 1 = plain fp16 inputs;  cluster: 1, 2 or 4 CTAs sharing the weight stream
 //   out    : accsum [S*G][128] (path 0) or hE_out [S*G][K][128] (path 1, may alias hE_in when he_shared == 0)
 extern "C" int pp_ipmp_edge_tc(const float* weights, int64_t layer, int64_t path, const float* wstream,
                                const float* geo, const int32_t* nbr, const float* mask_attend, int64_t G, int64_t K,

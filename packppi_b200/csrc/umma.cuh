@@ -7,6 +7,7 @@
 // i.e. SBO (next 8 rows) = 128 B and LBO (next 4 k-columns) = ROWS * 16 B.  A thread that owns one row writes 16-byte
 // units that are 16 B apart across the lanes of its warp: conflict-free 128-bit stores.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -93,6 +94,15 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
       "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
 }
+// 32 lanes x 16 consecutive columns (packed fp16 pairs: 32 k-elements of a TMEM A operand)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors
@@ -104,6 +114,33 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 // instruction descriptor: D = fp32, A = B = tf32, both K-major, M x N tile
 __host__ __device__ constexpr uint32_t idesc_tf32(uint32_t M, uint32_t N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// instruction descriptor: D = fp32, A = B = fp16 (format 0), both K-major, M x N tile; one instruction covers K = 16
+__host__ __device__ constexpr uint32_t idesc_f16(uint32_t M, uint32_t N) {
+  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// kind::f16 operands use the same canonical layout with 8 elements per 16-byte core-matrix row:
+//     byte_offset(row, k) = (k / 8) * (ROWS * 16) + (row / 8) * 128 + (row % 8) * 16 + (k % 8) * 2
+// A TMEM A operand holds two consecutive k-elements per 32-bit column (even k in the low half).
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T, one elected thread
@@ -139,6 +176,20 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
   lo = x - hi;
+}
+
+// Two fp32 values -> packed fp16 (hi, lo) pairs, x ~= hi + lo with both halves rounded to nearest: hi carries 11
+// mantissa bits, lo the next 11 (its sign lets the pair resolve 22+ bits).  hi*hi + hi*lo + lo*hi with fp32
+// accumulation reproduces an fp32 product to ~2^-22 at twice the tensor-core rate of kind::tf32 (K = 16 per
+// instruction).  fp16 range: |x| must stay below 65504 (an overflow gives inf - inf = NaN in lo, never a silently
+// wrong number); below 2^-14 the lo half is subnormal and the pair keeps an absolute 2^-25, which is why the weight
+// images are pre-scaled by a power of two (weights.py) while the O(1) activations are taken as they are.
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 }  // namespace umma

@@ -153,31 +153,42 @@ def pack_weights(sd, layout, total_floats):
     return blob
 
 
-def _tf32_split(w):
-    """w = hi + lo exactly, hi = w truncated to TF32 (low 13 mantissa bits cleared), lo left unrounded; same split as
-    split_tf32 in csrc/umma.cuh (truncation measured more accurate end to end than round-to-nearest)."""
-    hi = (w.contiguous().view(torch.int32) & -8192).view(torch.float32)
-    return hi, w - hi
+def _f16_split(w, scale):
+    """scale * w ~= hi + lo, both halves rounded to nearest fp16 (same split as split_f16x2 in csrc/umma.cuh); the
+    pair resolves 22 mantissa bits.  Returned as int16 bit patterns."""
+    ws = w.contiguous().to(torch.float32) * scale
+    hi = ws.to(torch.float16)
+    lo = (ws - hi.to(torch.float32)).to(torch.float16)
+    return hi.view(torch.int16), lo.view(torch.int16)
 
 
-def _umma_image(w):
-    """[128 rows, kc] K-major operand -> flat image in the no-swizzle core-matrix layout of csrc/umma.cuh:
-    float offset(row, k) = (k // 4) * 512 + (row // 8) * 32 + (row % 8) * 4 + k % 4."""
+def _f16_scale(w):
+    """Power of two that brings max |w| into [2^13, 2^14): hi stays far below the fp16 maximum and the lo halves of
+    all but vanishing weights stay in the normal fp16 range (the product is rescaled exactly in the epilogue)."""
+    m = float(w.abs().max())
+    return 1.0 if m == 0.0 else 2.0 ** (13 - math.floor(math.log2(m)))
+
+
+def _umma_image16(w):
+    """[128 rows, kc] K-major fp16 operand (int16 bit patterns) -> flat image in the no-swizzle core-matrix layout of
+    csrc/umma.cuh: element offset(row, k) = (k // 8) * 1024 + (row // 8) * 64 + (row % 8) * 8 + k % 8."""
     rows, kc = w.shape
-    assert rows == 128 and kc % 4 == 0
-    return w.reshape(16, 8, kc // 4, 4).permute(2, 0, 1, 3).contiguous().reshape(-1)
+    assert rows == 128 and kc % 8 == 0
+    return w.reshape(16, 8, kc // 8, 8).permute(2, 0, 1, 3).contiguous().reshape(-1)
 
 
 def pack_tc_stream(sd, stream_floats):
-    """Operand images for the tensor-core edge kernels (csrc/mpnn_tc.cu): [3 layers, 2 paths, stream_floats].
+    """Operand images for the tensor-core kernels (csrc/mpnn_tc.cu): [3 layers, 3 paths, stream_floats] float32 words
+    holding fp16 (hi, lo) image pairs followed by 8 floats 1 / scale of (G1, G2, G3, FFN-in, FFN-out).
 
     Per (layer, path) the chunks follow the kernel's consumption order, each chunk = hi image then lo image:
-      G1: W_in[:, h_E | pair geometry]  k = 0..167 in chunks of 32, 32, 32, 32, 32, 8
+      G1: W_in[:, h_E | pair geometry]  k = 0..167 zero-padded to 176, chunks of 32, 32, 32, 32, 32, 16
       G2: W_inter.0 (4 chunks), G3: W_out (4 chunks)
       FFN slices j = 0..3 (FFN-in = rows 128j..128j+127 of edge_dense.W_in, FFN-out = columns 128j..128j+127 of
       edge_dense.W_out, 4 chunks each), software-pipelined by one slice: in0, in1, out0, in2, out1, in3, out2, out3
-    The node path (path 0) uses G1 and G2 of node_message_fn only; the rest of its stream is zero.  Path 2 is the
-    per-residue node epilogue: node_message_fn.W_out (4 chunks) followed by node_dense in the same pipelined order."""
+    Every matrix is scaled by its own power of two (_f16_scale) before the split.  The node path (path 0) uses G1 and
+    G2 of node_message_fn only.  Path 2 is the per-residue node epilogue: node_message_fn.W_out (4 chunks) followed by
+    node_dense in the same pipelined order."""
     check_state_dict(sd)
     f = {k: v.detach().to("cpu", torch.float32) for k, v in sd.items()}
     out = torch.zeros(N_LAYERS, 3, stream_floats, dtype=torch.float32)
@@ -185,25 +196,34 @@ def pack_tc_stream(sd, stream_floats):
         p = f"mpnn.mpnn_layers.{l}."
         for path, fn in enumerate(("node_message_fn", "edge_message_fn", "node_message_fn")):
             Win = f[p + fn + ".W_in.weight"]
-            mats = [torch.cat([Win[:, 128:256], Win[:, 416:456]], 1), f[p + fn + ".W_inter.0.weight"]]
-            if path == 2:
-                mats = []
+            inv = torch.ones(8)
+            mats = []  # (matrix [128, k], scale)
+            if path != 2:
+                G1 = torch.cat([Win[:, 128:256], Win[:, 416:456], torch.zeros(128, 8)], 1)
+                G2 = f[p + fn + ".W_inter.0.weight"]
+                s1, s2 = _f16_scale(G1), _f16_scale(G2)
+                inv[0], inv[1] = 1.0 / s1, 1.0 / s2
+                mats += [(G1, s1), (G2, s2)]
             if path >= 1:
                 dense = "edge_dense" if path == 1 else "node_dense"
-                mats.append(f[p + fn + ".W_out.weight"])
+                G3 = f[p + fn + ".W_out.weight"]
                 Fi, Fo = f[p + dense + ".W_in.weight"], f[p + dense + ".W_out.weight"]
-                mats.append(Fi[0:128, :])
+                s3, si, so = _f16_scale(G3), _f16_scale(Fi), _f16_scale(Fo)
+                inv[2], inv[3], inv[4] = 1.0 / s3, 1.0 / si, 1.0 / so
+                mats.append((G3, s3))
+                mats.append((Fi[0:128, :], si))
                 for j in range(4):
                     if j + 1 < 4:
-                        mats.append(Fi[128 * (j + 1):128 * (j + 2), :])
-                    mats.append(Fo[:, 128 * j:128 * (j + 1)])
+                        mats.append((Fi[128 * (j + 1):128 * (j + 2), :], si))
+                    mats.append((Fo[:, 128 * j:128 * (j + 1)], so))
             pieces = []
-            for M in mats:
+            for M, scale in mats:
                 for k0 in range(0, M.shape[1], 32):
                     kc = min(32, M.shape[1] - k0)
-                    hi, lo = _tf32_split(M[:, k0:k0 + kc])
-                    pieces += [_umma_image(hi), _umma_image(lo)]
-            flat = torch.cat(pieces)
-            assert flat.numel() <= stream_floats
+                    hi, lo = _f16_split(M[:, k0:k0 + kc], scale)
+                    pieces += [_umma_image16(hi), _umma_image16(lo)]
+            flat = torch.cat(pieces).view(torch.float32)
+            assert flat.numel() <= stream_floats - 8
             out[l, path, :flat.numel()] = flat
+            out[l, path, stream_floats - 8:] = inv
     return out
