@@ -160,7 +160,8 @@ def run_reference(args):
 
 
 def workload_config(args):
-    return {"kernel_mode": os.environ.get("PACKPPI_B200_MODE", "tf32x3"),
+    return {"kernel_mode": os.environ.get("PACKPPI_B200_MODE", "f16x3"),
+            "kernel_node_epilogue": os.environ.get("PACKPPI_B200_NODE_EPILOGUE", "tc"),
             "kernel_cluster": int(os.environ.get("PACKPPI_B200_CLUSTER", "1")),
             "workload": f"sweep of {args.complexes} synthetic 2-chain complexes, L~U{{200..800}} (seed 64) x "
                         f"{N_SAMPLES} diffusion samples x {N_ODE} reverse-ODE steps, micro-batches of {MICRO} complexes; "
@@ -342,7 +343,7 @@ def main():
     d2h = sum(int(b.X.shape[0] * b.X.shape[1]) for b in micro_host) * N_SAMPLES * 4 * 4
 
     # instrumented pass: CUDA events around every launch of the dominant kernel (the per-edge edge update)
-    mode, cluster = model.kernel_mode, model.kernel_cluster
+    mode, cluster = model.engine(dev).mode, model.kernel_cluster
     pkey = "pp_ipmp_edge_edge" if mode == "fp32" else "pp_ipmp_edge_tc:edge"
     _lib.PROFILE = {pkey: []}
     t_pass = timed(micro_dev, False, 1)
@@ -357,8 +358,9 @@ def main():
         tflops = EDGE_KERNEL_FLOP_PER_RES * tot_rows / (tot_ms * 1e-3) / 1e12
         gbs = EDGE_KERNEL_BYTES_PER_RES * tot_rows / (tot_ms * 1e-3) / 1e9
         kname = {"fp32": "edge_edge_kernel (per-edge message MLP + FFN, fp32 FFMA on CUDA cores)",
-                 "tf32x3": "edge_tc_kernel<edge> (per-edge message MLP + FFN, tcgen05 split-TF32, 3 MMAs per product)",
-                 "tf32": "edge_tc_kernel<edge> (per-edge message MLP + FFN, tcgen05 plain TF32)"}[mode]
+                 "f16x3": "edge_tc_kernel<edge> (per-edge message MLP + FFN, tcgen05 kind::f16, split fp16 operand "
+                          "pairs: 3 MMAs per product, fp32 accumulation)",
+                 "f16": "edge_tc_kernel<edge> (per-edge message MLP + FFN, tcgen05 kind::f16, plain fp16 inputs)"}[mode]
         roof = {"kernel": kname, "bound": "tensor",
                 "achieved": tflops, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": tflops / peaks["tf_sust"],
                 "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",

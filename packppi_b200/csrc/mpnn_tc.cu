@@ -731,7 +731,7 @@ extern "C" int pp_ipmp_edge_tc(const float* weights, int64_t layer, int64_t path
   a.hE_in = hE_in; a.he_shared = (int)he_shared;
   a.A = wsA; a.Nn = wsN; a.pglob = wsP;
   a.out = out;
-  a.trace = g_tc_trace;
+  a.trace = path == 1 ? g_tc_trace : nullptr;  // the trace follows the edge-update kernel
   int rc;
 #define PP_TC_CASE(E, P, C) if (path == (E) && passes == (P) && cluster == (C)) rc = tc::launch<E, P, C>(a, stream); else
   PP_TC_CASE(0, 3, 1) PP_TC_CASE(0, 3, 2) PP_TC_CASE(0, 3, 4) PP_TC_CASE(0, 1, 1) PP_TC_CASE(0, 1, 2) PP_TC_CASE(0, 1, 4)

@@ -124,11 +124,20 @@ class Engine:
 
     # precision / execution modes of the per-edge message MLPs
     #   fp32   CUDA-core FFMA kernels (csrc/mpnn.cu), exact fp32
-    #   tf32x3 tcgen05 tensor cores, split-TF32 (3 MMAs per product, fp32-grade): parity mode of the tensor path
-    #   tf32   tcgen05 tensor cores, plain TF32: fast mode with a looser stated tolerance
-    MODES = ("fp32", "tf32x3", "tf32")
+    #   f16x3  tcgen05 tensor cores (kind::f16), every operand split into a rounded fp16 (hi, lo) pair, 3 MMAs per
+    #          product, fp32 accumulation: fp32-grade, the parity mode of the tensor path (default)
+    #   f16    tensor cores, hi halves only (11 mantissa bits, the precision of TF32): fast mode, looser stated tolerance
+    # node_epilogue: "tc" runs the per-residue node update (W_out, LayerNorm, FFN) on the tensor cores as well;
+    # "ffma" keeps it on the exact-fp32 CUDA-core kernel.  Measured on the fixtures (30-step trajectories, f16x3):
+    # tc 3.2e-5 rad max chi error for +9 % throughput, ffma 1.1e-5 rad (the fp32 mode itself: 1.2e-5); gate 1e-4.
+    MODES = ("fp32", "f16x3", "f16")
+    ALIASES = {"tf32x3": "f16x3", "tf32": "f16"}   # names of the first tensor-core implementation (split TF32)
 
-    def __init__(self, state_dict, device, mode="tf32x3", cluster=1):
+    def __init__(self, state_dict, device, mode="f16x3", cluster=1, node_epilogue="tc"):
+        mode = self.ALIASES.get(mode, mode)
+        if node_epilogue not in ("tc", "ffma"):
+            raise ValueError("node_epilogue must be 'tc' or 'ffma'")
+        self.node_epilogue = node_epilogue
         if mode not in self.MODES:
             raise ValueError(f"mode must be one of {self.MODES}")
         self.mode, self.cluster = mode, int(cluster)
@@ -186,7 +195,7 @@ class Engine:
                 _lib.call("pp_ipmp_layer", W, layer, *common, graph.msum, graph.mask, G, K, S, ws.hV, hE_in, shared,
                           ws.hE, 1 if edge else 0, ws.wsA, ws.wsN, ws.wsP, ws.wsAcc, kernels=5 if edge else 3)
                 continue
-            tcp = (3 if self.mode == "tf32x3" else 1, self.cluster)
+            tcp = (3 if self.mode == "f16x3" else 1, self.cluster)
             # the five kernels of a layer through their own entry points (instrumented fp32 mode, tensor-core modes)
             _lib.call("pp_ipmp_node_pre", W, layer, 0, *common, *size, ws.hV, ws.wsA, ws.wsN, ws.wsP, rows=S * G)
             if self.mode == "fp32":
@@ -195,13 +204,11 @@ class Engine:
             else:
                 _lib.call("pp_ipmp_edge_tc", W, layer, 0, self.wtc[layer, 0], *common, G, K, S, hE_in, shared, ws.wsA,
                           ws.wsN, ws.wsP, ws.wsAcc, *tcp, rows=S * G, tag="node")
-            if self.mode != "tf32":
-                # h_V feeds every later GEMM of the step: measured on the fixtures, running this per-residue epilogue
-                # in split TF32 raises the 30-step chi error from 1.9e-5 to 7e-5 rad (gate 1e-4) for 3 % of speed,
-                # so the parity modes keep it on the exact-fp32 FFMA kernel
+            if self.mode == "fp32" or self.node_epilogue == "ffma":
                 _lib.call("pp_ipmp_node_post", W, layer, *common, graph.msum, *size, ws.wsAcc, ws.hV, rows=S * G)
             else:
-                # fast mode: tensor cores, but split TF32 even here (plain TF32 would triple the chi error)
+                # always the 3-pass split, also in the fast mode: h_V feeds every later GEMM of the step and plain
+                # fp16 inputs here would triple the chi error
                 _lib.call("pp_ipmp_node_post_tc", W, layer, self.wtc[layer, 2], graph.msum, graph.mask, G, K, S,
                           ws.wsAcc, ws.hV, 3, self.cluster, rows=S * G)
             if edge:

@@ -84,22 +84,24 @@ class _PackedModule(nn.Module):
     """Caches an Engine (packed weights on one device) and rebuilds it when a parameter changes.
 
     `kernel_mode` selects how the per-edge message MLPs run (engine.Engine.MODES): "fp32" = CUDA-core FFMA (exact),
-    "tf32x3" = tcgen05 tensor cores with split TF32 (fp32-grade), "tf32" = tensor cores, plain TF32 (fast, looser
-    tolerance).  `kernel_cluster` = CTAs per cluster sharing the weight stream in the tensor-core modes (1, 2, 4).
-    Defaults come from the environment (PACKPPI_B200_MODE, PACKPPI_B200_CLUSTER)."""
-    kernel_mode = os.environ.get("PACKPPI_B200_MODE", "tf32x3")
+    "f16x3" = tcgen05 tensor cores with split fp16 operand pairs (fp32-grade, default), "f16" = tensor cores, plain
+    fp16 inputs (fast, looser tolerance).  `kernel_cluster` = CTAs per cluster sharing the weight stream in the
+    tensor-core modes (1, 2, 4).  `kernel_node_epilogue` = "tc" | "ffma": where the per-residue node update runs.
+    Defaults come from the environment (PACKPPI_B200_MODE, PACKPPI_B200_CLUSTER, PACKPPI_B200_NODE_EPILOGUE)."""
+    kernel_mode = os.environ.get("PACKPPI_B200_MODE", "f16x3")
     kernel_cluster = int(os.environ.get("PACKPPI_B200_CLUSTER", "1"))
+    kernel_node_epilogue = os.environ.get("PACKPPI_B200_NODE_EPILOGUE", "tc")
 
     def _full_state_dict(self):
         raise NotImplementedError
 
     def engine(self, device):
         device = torch.device(device)
-        sig = (str(device), self.kernel_mode, self.kernel_cluster) + tuple((p.data_ptr(), p._version)
+        sig = (str(device), self.kernel_mode, self.kernel_cluster, self.kernel_node_epilogue) + tuple((p.data_ptr(), p._version)
                                                                             for p in self.parameters())
         if getattr(self, "_engine_sig", None) != sig:
             object.__setattr__(self, "_engine_obj", Engine(self._full_state_dict(), device, self.kernel_mode,
-                                                           self.kernel_cluster))
+                                                           self.kernel_cluster, self.kernel_node_epilogue))
             object.__setattr__(self, "_engine_sig", sig)
         return self._engine_obj
 
