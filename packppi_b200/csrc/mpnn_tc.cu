@@ -48,7 +48,7 @@ constexpr int kChunksEdge = 6 + 4 + 4 + 4 * 8;   // + G3, 4 x (FFN-in slice, FFN
 constexpr long long kImageFloats = 2LL * 128 * (176 + 128 + 128 + 4 * 256) * 2 / 4;
 constexpr long long kStreamFloats = kImageFloats + 8;
 
-constexpr size_t kBarBytes = (2 * kSA + 2 * kSB + 2 + 1) * 8;
+constexpr size_t kBarBytes = (2 * kSA + 2 * kSB + 2 + 2) * 8;
 // per-column parameters staged in shared memory (floats): b2, b3, LN2 gain/bias, FFN b_in (512), b_out, LN3 gain/bias
 constexpr int kP_B2 = 0, kP_B3 = 128, kP_LN2G = 256, kP_LN2B = 384, kP_BIN = 512, kP_BOUT = 1024, kP_LN3G = 1152,
               kP_LN3B = 1280, kParamFloats = 1408;
@@ -138,9 +138,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
   uint64_t* b_full = a_empty + kSA;
   uint64_t* b_empty = b_full + kSB;
   uint64_t* acc_full = b_empty + kSB;  // [2]
-  uint64_t* wk_done = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wk_done + 1);
-  float* prm = reinterpret_cast<float*>(wk_done + 3);
+  uint64_t* wk_done = acc_full + 2;     // FFN hand-offs within a tile (e in TMEM, slice j read out)
+  uint64_t* tile_done = wk_done + 1;    // the workers have read out everything a tile left in TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_done + 1);
+  float* prm = reinterpret_cast<float*>(tile_done + 3);
   float* red = prm + kParamFloats;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -157,6 +158,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
     mbar_init(&acc_full[0], 1);
     mbar_init(&acc_full[1], 1);
     mbar_init(wk_done, 256);
+    mbar_init(tile_done, 256);
     mbar_fence_init();
   }
   {  // stage the per-column parameters
@@ -172,8 +174,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
   if (CLUSTER > 1) cluster_sync_all();  // every CTA's barriers exist before any remote arrive / multicast
   fence_after_sync();
   const uint32_t tmem = *tmem_slot;
-  // TMEM columns: two accumulators, e in fp32 (residual; before that the raw h_E row), e as packed fp16 hi / lo
-  const uint32_t ACC0 = tmem, ACC1 = tmem + 128, E32 = tmem + 256, EH = tmem + 384, EL = tmem + 448;
+  // TMEM columns: two accumulators and two operand regions; per tile one region holds the raw h_E row and later e
+  // in fp32 (residual), the other e as packed fp16 (hi: 64 columns, lo: 64 columns); the roles swap every tile
+  const uint32_t ACC0 = tmem, ACC1 = tmem + 128, R0 = tmem + 256, R1 = tmem + 384;
 
   if (warp == 9) {
     // ------------------------------------------------------------------ weight loader
@@ -205,9 +208,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       Ring ra{0, 0}, rbq{0, 0};
-      uint32_t wk_phase = 0;
-      auto chunk = [&](bool ss, uint32_t acc, uint32_t a_col, int kc, bool fresh) {
-        // pass 0: hi * hi, pass 1: hi * lo, pass 2: lo * hi; a_col = first packed TMEM column of a TS chunk
+      uint32_t wk_phase = 0, td_phase = 0;
+      // ss: A from the shared-memory ring; otherwise a_tm = TMEM address of the packed hi half of the chunk (lo: + 64)
+      auto chunk = [&](bool ss, uint32_t acc, uint32_t a_tm, int kc, bool fresh) {
+        // pass 0: hi * hi, pass 1: hi * lo, pass 2: lo * hi
         if (ss) mbar_wait(&a_full[ra.idx], ra.phase);
         const uint32_t as = smem_u32(Aring + ra.idx * kSlotBytes);
         mbar_wait(&b_full[rbq.idx], rbq.phase);
@@ -221,49 +225,63 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
             const uint64_t bd = smem_desc(bs + bo + (kk / 8) * kLbo, kLbo, kSbo);
             const uint32_t accum = (fresh && p == 0 && kk == 0) ? 0u : 1u;
             if (ss) mma_f16_ss(acc, smem_desc(as + ao + (kk / 8) * kLbo, kLbo, kSbo), bd, kIdesc, accum);
-            else mma_f16_ts(acc, ((p == 2) ? EL : EH) + a_col + kk / 2, bd, kIdesc, accum);
+            else mma_f16_ts(acc, a_tm + ((p == 2) ? 64 : 0) + kk / 2, bd, kIdesc, accum);
           }
         }
         if (CLUSTER == 1) mma_commit(&b_empty[rbq.idx]); else mma_commit_mc(&b_empty[rbq.idx], kMask);
         rbq.next(kSB);
         if (ss) { mma_commit(&a_empty[ra.idx]); ra.next(kSA); }
       };
+      auto wait_workers = [&]() { mbar_wait(wk_done, wk_phase); wk_phase ^= 1; fence_after_sync(); };
+      // first GEMM of a tile: G1 = [h_E | pair] (176 wide) of the message MLP, or W3 of the node epilogue
+      auto head = [&](uint32_t acc, int bar) {
+        if (!POST) { for (int c = 0; c < 6; ++c) chunk(true, acc, 0, c == 5 ? kPairKC : kKC, c == 0); }
+        else       { for (int c = 0; c < 4; ++c) chunk(true, acc, 0, kKC, c == 0); }
+        mma_commit(&acc_full[bar]);
+      };
+      // Tiles are software-pipelined: the head GEMM of tile it+1 is issued before the workers run the last epilogue of
+      // tile it.  In the EDGE modes the roles of the two accumulators (X: head, G3, FFN-out; Y: G2, FFN-in) and of
+      // the two TMEM operand regions swap with the parity of the tile so that nothing live is overwritten.
+      head(ACC0, 0);
       for (int it = 0; it < niter; ++it) {
+        const int par = EDGE ? (it & 1) : 0;
+        const uint32_t X = par ? ACC1 : ACC0, Y = par ? ACC0 : ACC1;
+        const int xb = par, yb = par ^ 1;
+        const uint32_t PK = par ? R0 : R1;  // packed fp16 (hi | lo) image of e
+        if (it > 0) {  // the previous tile has been read out completely: its X (this tile's Y) may be overwritten
+          mbar_wait(tile_done, td_phase); td_phase ^= 1; fence_after_sync();
+        }
         if (!POST) {
-          // G1: [h_E | pair] (168) -> ACC0
-          for (int c = 0; c < 6; ++c) chunk(true, ACC0, 0, c == 5 ? kPairKC : kKC, c == 0);
-          mma_commit(&acc_full[0]);
-          // G2 -> ACC1
-          for (int c = 0; c < 4; ++c) chunk(true, ACC1, 0, kKC, c == 0);
-          mma_commit(&acc_full[1]);
+          for (int c = 0; c < 4; ++c) chunk(true, Y, 0, kKC, c == 0);  // G2
+          mma_commit(&acc_full[yb]);
         }
-        if (EDGE) {
-          // G3 -> ACC0
-          for (int c = 0; c < 4; ++c) chunk(true, ACC0, 0, kKC, c == 0);
-          mma_commit(&acc_full[0]);
-          // FFN, software-pipelined by one slice: while the workers turn slice j into the A operand of FFN-out j,
-          // the tensor pipe runs FFN-out j-1 and FFN-in j+1.  A whole hidden slice (4 chunks) is parked in the A ring.
-          mbar_wait(wk_done, wk_phase);  // e is in TMEM, ACC0 / ACC1 are drained
-          wk_phase ^= 1;
-          fence_after_sync();
-          for (int c = 0; c < 4; ++c) chunk(false, ACC1, c * (kKC / 2), kKC, c == 0);  // FFN-in slice 0: A = e from TMEM
-          mma_commit(&acc_full[1]);
-          for (int j = 0; j < 4; ++j) {
-            if (j + 1 < 4) {
-              mbar_wait(wk_done, wk_phase);  // slice j has been read out of ACC1 (and published)
-              wk_phase ^= 1;
-              fence_after_sync();
-              for (int c = 0; c < 4; ++c) chunk(false, ACC1, c * (kKC / 2), kKC, c == 0);  // FFN-in slice j+1
-              mma_commit(&acc_full[1]);
-            }
-            for (int c = 0; c < 4; ++c) chunk(true, ACC0, 0, kKC, j == 0 && c == 0);  // FFN-out slice j accumulates
+        if (!EDGE) {
+          // G2's operand chunks exist only once every worker has drained ACC0, so the next G1 may follow directly
+          if (it + 1 < niter) head(ACC0, 0);
+          continue;
+        }
+        if (!POST) {
+          for (int c = 0; c < 4; ++c) chunk(true, X, 0, kKC, c == 0);  // G3
+          mma_commit(&acc_full[xb]);
+        }
+        // FFN, software-pipelined by one slice: while the workers turn slice j into the A operand of FFN-out j,
+        // the tensor pipe runs FFN-out j-1 and FFN-in j+1
+        wait_workers();  // e is in TMEM, X / Y are drained
+        for (int c = 0; c < 4; ++c) chunk(false, Y, PK + c * (kKC / 2), kKC, c == 0);  // FFN-in slice 0: A = e (TMEM)
+        mma_commit(&acc_full[yb]);
+        for (int j = 0; j < 4; ++j) {
+          if (j + 1 < 4) {
+            wait_workers();  // slice j has been read out of Y
+            for (int c = 0; c < 4; ++c) chunk(false, Y, PK + c * (kKC / 2), kKC, c == 0);  // FFN-in slice j+1
+            mma_commit(&acc_full[yb]);
           }
-          mma_commit(&acc_full[0]);
+          for (int c = 0; c < 4; ++c) chunk(true, X, 0, kKC, j == 0 && c == 0);  // FFN-out slice j accumulates
         }
-        // the workers have drained both accumulators of this tile before the next tile's G1 overwrites them
-        mbar_wait(wk_done, wk_phase);
-        wk_phase ^= 1;
-        fence_after_sync();
+        mma_commit(&acc_full[xb]);
+        if (it + 1 < niter) {
+          wait_workers();  // slice 3 has been read out of Y, which becomes the X of the next tile
+          head(Y, yb);
+        }
       }
     }
   } else {
@@ -275,7 +293,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
     uint32_t accph[2] = {0, 0};
     const float* wsc = a.wstream + kImageFloats;  // 1 / scale of the weight images
     const float sG1 = wsc[0], sG2 = wsc[1], sG3 = wsc[2], sFI = wsc[3], sFO = wsc[4];
-    int qbase = 0;  // running A-chunk counter (ring position persists across tiles)
+    constexpr int kChunksTile = POST ? 20 : (EDGE ? 30 : 10);  // A chunks per tile
+    const bool tracer = a.trace && blockIdx.x == 0 && tid == 0;
+    int stamp_i = 0;
+    auto stamp = [&](bool first_tile) {
+      if (tracer && first_tile) a.trace[stamp_i++] = clock64();
+    };
 
     struct RowCtx {  // where this thread's edge row of a tile lives
       int r, rr, g, jrow;
@@ -305,138 +328,138 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
       c.hrow = a.hE_in + ((size_t)(a.he_shared ? c.g : c.rr) * K + (c.in_range ? k : 0)) * 128;
       return c;
     };
-    auto load_h = [&](const RowCtx& c, float4 (&h)[2][8]) {
-#pragma unroll
-      for (int t = 0; t < 2; ++t)
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-          h[t][u] = c.in_range ? *reinterpret_cast<const float4*>(c.hrow + (grp + 2 * t) * 32 + u * 4)
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
-    };
     auto row_total = [&](float partial, int which) -> float {  // sum over the two threads that share a row
       red[(which * 2 + grp) * 128 + m] = partial;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       return red[(which * 2) * 128 + m] + red[(which * 2 + 1) * 128 + m];
     };
-
     auto prefetch_h = [&](const RowCtx& c) {  // pull the next tile's h_E lines into L2 (no registers held)
       if (c.in_range) {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(c.hrow + grp * 32));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(c.hrow + (grp + 2) * 32));
       }
     };
+    // A chunk number q of the kernel-wide schedule -> ring slot q % kSA, (q / kSA)-th use of that slot
+    auto publish = [&](int q, const float* vals, int kc) {
+      const int slot = q % kSA;
+      mbar_wait(&a_empty[slot], ((q / kSA) & 1) ^ 1);
+      put_chunk<PASSES>(Aring + slot * kSlotBytes, m, vals, kc);
+      fence_async_smem();
+      mbar_arrive(&a_full[slot]);
+    };
+    auto load_acc = [&](uint32_t acc, int c, float (&dst)[32]) {
+      uint32_t u[32];
+      tmem_ld32(acc + lane_base + c * 32, u);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) dst[i] = __uint_as_float(u[i]);
+    };
+    auto store_tmem = [&](uint32_t col, const float* vals) {
+      uint32_t u[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) u[i] = __float_as_uint(vals[i]);
+      tmem_st32(col + lane_base, u);
+    };
 
-    RowCtx cx = row_ctx(0);
-    float4 hpre[2][8];  // h_E columns of this thread for the tile about to start
-    if (!EDGE) load_h(cx, hpre);
-
-    for (int it = 0; it < niter; ++it) {
-      if (EDGE) load_h(cx, hpre);
-      const bool on = cx.on, in_range = cx.in_range;
-      const int r = cx.r, rr = cx.rr;
+    // ---- first A operand of a tile (chunks qb .. qb+5): h_E row (4 chunks) and the pair geometry (32 + 16 columns);
+    //      node epilogue: the residue's summed messages scaled by 1/K (the mean over K commutes with W3), 4 chunks.
+    //      Edge update: the raw row is also parked in the TMEM region `stash` for the residual, instead of reading
+    //      it from global memory a second time (a row-per-thread read costs 32 L1 wavefronts per instruction).
+    auto first_operand = [&](const RowCtx& c, int qb, uint32_t stash) {
       float v[32];
-      int stamp_i = 0;
-      auto stamp = [&]() {
-        if (a.trace && blockIdx.x == 0 && it == 0 && tid == 0) a.trace[stamp_i] = clock64();
-        ++stamp_i;
-      };
-      stamp();  // 0: tile start
-      // A chunk number q of the tile's fixed schedule -> ring slot q % kSA, (q / kSA)-th use of that slot
-      auto publish = [&](int qrel, const float* vals, int kc) {
-        const int q = qbase + qrel;
-        const int slot = q % kSA;
-        mbar_wait(&a_empty[slot], ((q / kSA) & 1) ^ 1);
-        put_chunk<PASSES>(Aring + slot * kSlotBytes, m, vals, kc);
-        fence_async_smem();
-        mbar_arrive(&a_full[slot]);
-      };
-      auto load_acc = [&](uint32_t acc, int c, float (&dst)[32]) {
-        uint32_t u[32];
-        tmem_ld32(acc + lane_base + c * 32, u);
-        tmem_ld_wait();
+      float4 h[2][8];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) dst[i] = __uint_as_float(u[i]);
-      };
-      auto store_tmem = [&](uint32_t col, const float* vals) {
-        uint32_t u[32];
+      for (int t = 0; t < 2; ++t)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) u[i] = __float_as_uint(vals[i]);
-        tmem_st32(col + lane_base, u);
-      };
-
-      // ---- first A operand: h_E row (chunks 0-3) and the pair geometry (chunk 4: 32 columns, chunk 5: 8 columns);
-      //      node epilogue: the residue's summed messages scaled by 1/K (the mean over K commutes with W3)
+        for (int u = 0; u < 8; ++u)
+          h[t][u] = c.in_range ? *reinterpret_cast<const float4*>(c.hrow + (grp + 2 * t) * 32 + u * 4)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
       if (POST) {
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            v[u * 4] = hpre[t][u].x * a.in_scale; v[u * 4 + 1] = hpre[t][u].y * a.in_scale;
-            v[u * 4 + 2] = hpre[t][u].z * a.in_scale; v[u * 4 + 3] = hpre[t][u].w * a.in_scale;
+            v[u * 4] = h[t][u].x * a.in_scale; v[u * 4 + 1] = h[t][u].y * a.in_scale;
+            v[u * 4 + 2] = h[t][u].z * a.in_scale; v[u * 4 + 3] = h[t][u].w * a.in_scale;
           }
-          publish(grp + 2 * t, v, kKC);
+          publish(qb + grp + 2 * t, v, kKC);
+        }
+        return;
+      }
+      const float4* fr4 = reinterpret_cast<const float4*>(a.geo + (size_t)c.g * PP_GEO_STRIDE);
+      const float4* pi4 = reinterpret_cast<const float4*>(a.pglob + (size_t)c.rr * 24);
+      const float4* pj4 = reinterpret_cast<const float4*>(a.pglob + (size_t)c.jrow * 24);
+      float fr[12], pi[24], pj[24];
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        float4 x = pj4[u];
+        pj[u * 4] = x.x; pj[u * 4 + 1] = x.y; pj[u * 4 + 2] = x.z; pj[u * 4 + 3] = x.w;
+      }
+      if (grp == 0) {
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          float4 x = fr4[u];
+          fr[u * 4] = x.x; fr[u * 4 + 1] = x.y; fr[u * 4 + 2] = x.z; fr[u * 4 + 3] = x.w;
         }
       } else {
-        const float4* fr4 = reinterpret_cast<const float4*>(a.geo + (size_t)cx.g * PP_GEO_STRIDE);
-        const float4* pi4 = reinterpret_cast<const float4*>(a.pglob + (size_t)rr * 24);
-        const float4* pj4 = reinterpret_cast<const float4*>(a.pglob + (size_t)cx.jrow * 24);
-        float fr[12], pi[24], pj[24];
 #pragma unroll
         for (int u = 0; u < 6; ++u) {
-          float4 x = pj4[u];
-          pj[u * 4] = x.x; pj[u * 4 + 1] = x.y; pj[u * 4 + 2] = x.z; pj[u * 4 + 3] = x.w;
+          float4 x = pi4[u];
+          pi[u * 4] = x.x; pi[u * 4 + 1] = x.y; pi[u * 4 + 2] = x.z; pi[u * 4 + 3] = x.w;
         }
-        if (grp == 0) {
-#pragma unroll
-          for (int u = 0; u < 3; ++u) {
-            float4 x = fr4[u];
-            fr[u * 4] = x.x; fr[u * 4 + 1] = x.y; fr[u * 4 + 2] = x.z; fr[u * 4 + 3] = x.w;
-          }
-        } else {
-#pragma unroll
-          for (int u = 0; u < 6; ++u) {
-            float4 x = pi4[u];
-            pi[u * 4] = x.x; pi[u * 4 + 1] = x.y; pi[u * 4 + 2] = x.z; pi[u * 4 + 3] = x.w;
-          }
-        }
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            v[u * 4] = hpre[t][u].x; v[u * 4 + 1] = hpre[t][u].y; v[u * 4 + 2] = hpre[t][u].z; v[u * 4 + 3] = hpre[t][u].w;
-          }
-          // edge update: keep the raw row for the residual in the (still unused) FFN-operand region of TMEM instead of
-          // reading it from global memory a second time (a row-per-thread read costs 32 L1 wavefronts per instruction)
-          if (MODE == 1) store_tmem(E32 + (grp + 2 * t) * 32, v);
-          publish(grp + 2 * t, v, kKC);
-        }
-        if (MODE == 1) tmem_st_wait();
-        float geo[32];
-#pragma unroll
-        for (int i = 8; i < kPairKC; ++i) geo[i] = 0.f;  // zero padding of the distance chunk (group 1)
-#pragma unroll
-        for (int pt = 0; pt < 8; ++pt) {
-          const float jx = pj[pt * 3], jy = pj[pt * 3 + 1], jz = pj[pt * 3 + 2];
-          if (grp == 0) {  // neighbour points in the local frame and their norms   (layers.py:93-97)
-            float dx = jx - fr[9], dy = jy - fr[10], dz = jz - fr[11];
-            float qx = fr[0] * dx + fr[3] * dy + fr[6] * dz;
-            float qy = fr[1] * dx + fr[4] * dy + fr[7] * dz;
-            float qz = fr[2] * dx + fr[5] * dy + fr[8] * dz;
-            geo[pt * 3] = qx; geo[pt * 3 + 1] = qy; geo[pt * 3 + 2] = qz;
-            geo[24 + pt] = sqrtf(qx * qx + qy * qy + qz * qz + 1e-8f);
-          } else {         // distances between the global points   (layers.py:99-103)
-            float gx = pi[pt * 3] - jx, gy = pi[pt * 3 + 1] - jy, gz = pi[pt * 3 + 2] - jz;
-            geo[pt] = sqrtf(gx * gx + gy * gy + gz * gz + 1e-8f);
-          }
-        }
-        if (grp == 0) publish(4, geo, kKC); else publish(5, geo, kPairKC);
       }
-      stamp();  // 1: first operand published
-      // next tile's row: resolve it early so that its addresses are ready when the prefetch is issued
-      RowCtx nx = cx;
-      if (it + 1 < niter) nx = row_ctx(it + 1);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          v[u * 4] = h[t][u].x; v[u * 4 + 1] = h[t][u].y; v[u * 4 + 2] = h[t][u].z; v[u * 4 + 3] = h[t][u].w;
+        }
+        if (MODE == 1) store_tmem(stash + (grp + 2 * t) * 32, v);
+        publish(qb + grp + 2 * t, v, kKC);
+      }
+      if (MODE == 1) tmem_st_wait();
+      float geo[32];
+#pragma unroll
+      for (int i = 8; i < kPairKC; ++i) geo[i] = 0.f;  // zero padding of the distance chunk (group 1)
+#pragma unroll
+      for (int pt = 0; pt < 8; ++pt) {
+        const float jx = pj[pt * 3], jy = pj[pt * 3 + 1], jz = pj[pt * 3 + 2];
+        if (grp == 0) {  // neighbour points in the local frame and their norms   (layers.py:93-97)
+          float dx = jx - fr[9], dy = jy - fr[10], dz = jz - fr[11];
+          float qx = fr[0] * dx + fr[3] * dy + fr[6] * dz;
+          float qy = fr[1] * dx + fr[4] * dy + fr[7] * dz;
+          float qz = fr[2] * dx + fr[5] * dy + fr[8] * dz;
+          geo[pt * 3] = qx; geo[pt * 3 + 1] = qy; geo[pt * 3 + 2] = qz;
+          geo[24 + pt] = sqrtf(qx * qx + qy * qy + qz * qz + 1e-8f);
+        } else {         // distances between the global points   (layers.py:99-103)
+          float gx = pi[pt * 3] - jx, gy = pi[pt * 3 + 1] - jy, gz = pi[pt * 3 + 2] - jz;
+          geo[pt] = sqrtf(gx * gx + gy * gy + gz * gz + 1e-8f);
+        }
+      }
+      if (grp == 0) publish(qb + 4, geo, kKC); else publish(qb + 5, geo, kPairKC);
+    };
 
-      // ---- epilogue of G1: x1 = relu(acc + A_i + N_j); the two gathered rows are fetched before the wait
+    RowCtx cx = row_ctx(0);
+    int qbase = 0;  // first A chunk of the current tile (ring positions persist across tiles)
+    stamp(true);  // 0: start
+    first_operand(cx, 0, R0);
+    stamp(true);  // 1: first operand of tile 0 published
+
+    for (int it = 0; it < niter; ++it) {
+      const bool t0 = it == 0;
+      const int par = EDGE ? (it & 1) : 0;
+      const uint32_t X = par ? ACC1 : ACC0, Y = par ? ACC0 : ACC1;
+      const int xb = par, yb = par ^ 1;
+      const uint32_t RE = par ? R1 : R0;   // raw h_E row, later e in fp32 (residual)
+      const uint32_t PK = par ? R0 : R1;   // e as packed fp16: hi in columns [0, 64), lo in [64, 128)
+      const bool on = cx.on, in_range = cx.in_range;
+      const int r = cx.r, rr = cx.rr;
+      const bool more = it + 1 < niter;
+      RowCtx nx = cx;
+      if (more) nx = row_ctx(it + 1);
+      float v[32];
+
+      // ---- epilogue of the head GEMM G1: x1 = relu(acc + A_i + N_j); the two gathered rows are fetched before the wait
       if (!POST) {
         const float* Ai = a.A + (size_t)rr * 128;
         const float* Nj = a.Nn + (size_t)cx.jrow * 128;
@@ -449,12 +472,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
             float4 y = *reinterpret_cast<const float4*>(Nj + (grp + 2 * t) * 32 + u * 4);
             an[t][u] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
           }
-        mbar_wait(&acc_full[0], accph[0]); accph[0] ^= 1;
+        mbar_wait(&acc_full[xb], accph[xb]); accph[xb] ^= 1;
         fence_after_sync();
-        stamp();  // 2: G1 complete
+        stamp(t0);  // 2: G1 complete
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-          load_acc(ACC0, grp + 2 * t, v);
+          load_acc(X, grp + 2 * t, v);
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             v[u * 4 + 0] = fmaxf(fmaf(v[u * 4 + 0], sG1, an[t][u].x), 0.f);
@@ -462,20 +485,18 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
             v[u * 4 + 2] = fmaxf(fmaf(v[u * 4 + 2], sG1, an[t][u].z), 0.f);
             v[u * 4 + 3] = fmaxf(fmaf(v[u * 4 + 3], sG1, an[t][u].w), 0.f);
           }
-          publish(6 + grp + 2 * t, v, kKC);
+          publish(qbase + 6 + grp + 2 * t, v, kKC);
         }
+        stamp(t0);  // 3: x1 published
       }
-      stamp();  // 3: x1 published
-      if (!EDGE && it + 1 < niter) load_h(nx, hpre);  // node message path: start fetching the next tile's h_E now
 
-      // ---- epilogue of G2: x2 = relu(acc + b2)
-      if (!POST) {
+      if (!EDGE) {
+        // node message path: the next tile's first operand is built while G2 runs; its G1 then overlaps the reduction
+        if (more) first_operand(nx, qbase + kChunksTile, 0);
         mbar_wait(&acc_full[1], accph[1]); accph[1] ^= 1;
         fence_after_sync();
-      }
-      stamp();  // 4: G2 complete
-      if (!EDGE) {
-        // node path: masked sum over the 32 edges of the residue (= the 32 lanes of this warp), layers.py:125-127
+        stamp(t0);  // 4: G2 complete
+        // masked sum over the 32 edges of the residue (= the 32 lanes of this warp), layers.py:125-127
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           const int c = grp + 2 * t;
@@ -496,20 +517,25 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
           }
           if (r < R) a.out[(size_t)r * 128 + c * 32 + lane] = v[0];
         }
+        stamp(t0);  // 5: sums written
       } else {
+        // ---- epilogue of G2: x2 = relu(acc + b2)
         if (!POST) {
+          mbar_wait(&acc_full[yb], accph[yb]); accph[yb] ^= 1;
+          fence_after_sync();
+          stamp(t0);  // 4: G2 complete
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             const int c = grp + 2 * t;
-            load_acc(ACC1, c, v);
+            load_acc(Y, c, v);
             const float* b = prm + kP_B2 + c * 32;
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(fmaf(v[i], sG2, b[i]), 0.f);
-            publish(10 + c, v, kKC);
+            publish(qbase + 10 + c, v, kKC);
           }
+          stamp(t0);  // 5: x2 published
         }
-        stamp();  // 5: x2 published
-        // ---- epilogue of G3: e = LN2(h_E + mask * (acc + b3))   (layers.py:139-142); e -> TMEM as (hi, lo)
+        // ---- epilogue of G3: e = LN2(h_E + mask * (acc + b3))   (layers.py:139-142); e -> TMEM (fp32 and packed fp16)
         {
           float4 h[2][8];
           if (POST) {  // residual = h_V of the residue; b3 enters scaled by the mean attention mask (layers.py:125-128)
@@ -521,9 +547,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
           }
           const float bscale = POST ? a.msum[cx.g] : 1.f;
           const bool gate = POST ? true : on;
-          mbar_wait(&acc_full[0], accph[0]); accph[0] ^= 1;
+          mbar_wait(&acc_full[xb], accph[xb]); accph[xb] ^= 1;
           fence_after_sync();
-          stamp();  // 6: G3 complete
+          stamp(t0);  // 6: G3 complete
           float x[2][32];
           float sum = 0.f;
 #pragma unroll
@@ -535,9 +561,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
                 x[t][u * 4] = h[t][u].x; x[t][u * 4 + 1] = h[t][u].y; x[t][u * 4 + 2] = h[t][u].z; x[t][u * 4 + 3] = h[t][u].w;
               }
             } else {
-              load_acc(E32, c, x[t]);  // the raw h_E row stashed during the first-operand build
+              load_acc(RE, c, x[t]);  // the raw h_E row parked by first_operand
             }
-            load_acc(ACC0, c, v);
+            load_acc(X, c, v);
             const float* b = prm + kP_B3 + c * 32;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -562,47 +588,51 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
             for (int i = 0; i < 32; ++i) v[i] = (x[t][i] - mean) * rstd * gm[i] + bt[i];
 #pragma unroll
             for (int i = 0; i < 16; ++i) split_f16x2(v[2 * i], v[2 * i + 1], eh[i], el[i]);
-            store_tmem(E32 + c * 32, v);
-            tmem_st16(EH + lane_base + c * 16, eh);
-            if (PASSES == 3) tmem_st16(EL + lane_base + c * 16, el);
+            store_tmem(RE + c * 32, v);
+            tmem_st16(PK + lane_base + c * 16, eh);
+            if (PASSES == 3) tmem_st16(PK + 64 + lane_base + c * 16, el);
           }
           tmem_st_wait();
           fence_before_sync();
           mbar_arrive(wk_done);
-          stamp();  // 7: e in TMEM
+          stamp(t0);  // 7: e in TMEM
         }
-        if (it + 1 < niter) prefetch_h(nx);
+        if (more) prefetch_h(nx);
         // ---- FFN: hidden slice j = relu(acc + b_in[j]) -> the four A chunks of FFN-out slice j
         for (int j = 0; j < 4; ++j) {
-          mbar_wait(&acc_full[1], accph[1]); accph[1] ^= 1;
+          mbar_wait(&acc_full[yb], accph[yb]); accph[yb] ^= 1;
           fence_after_sync();
-          stamp();  // 8 + 2j: FFN-in slice j complete
+          stamp(t0);  // 8 + 2j: FFN-in slice j complete
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             const int c = grp + 2 * t;
-            load_acc(ACC1, c, v);
-            if (t == 1 && j < 3) {  // ACC1 is drained for this thread: the next FFN-in slice may overwrite it
+            load_acc(Y, c, v);
+            if (t == 1) {  // Y is drained for this thread: the next FFN-in slice / the next tile's head may overwrite it
               fence_before_sync();
               mbar_arrive(wk_done);
             }
             const float* b = prm + kP_BIN + j * 128 + c * 32;
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(fmaf(v[i], sFI, b[i]), 0.f);
-            publish((POST ? 4 : 14) + 4 * j + c, v, kKC);
+            publish(qbase + (POST ? 4 : 14) + 4 * j + c, v, kKC);
           }
-          stamp();  // 9 + 2j: hidden slice j published
+          stamp(t0);  // 9 + 2j: hidden slice j published
         }
+        // ---- the next tile's first operand is built while FFN-out drains; its head GEMM then overlaps the final
+        //      LayerNorm and the stores below.  PK is free: the workers have seen FFN-in 3 complete.
+        if (more) first_operand(nx, qbase + kChunksTile, PK);
+        stamp(t0);  // 16: next first operand published
         // ---- final: y = LN3(e + acc + b_out) * mask   (layers.py:143-146)
-        mbar_wait(&acc_full[0], accph[0]); accph[0] ^= 1;
+        mbar_wait(&acc_full[xb], accph[xb]); accph[xb] ^= 1;
         fence_after_sync();
-        stamp();  // 16: FFN-out complete
+        stamp(t0);  // 17: FFN-out complete
         float y[2][32];
         float sum = 0.f;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           const int c = grp + 2 * t;
-          load_acc(E32, c, y[t]);
-          load_acc(ACC0, c, v);
+          load_acc(RE, c, y[t]);
+          load_acc(X, c, v);
           const float* b = prm + kP_BOUT + c * 32;
 #pragma unroll
           for (int i = 0; i < 32; ++i) { y[t][i] += fmaf(v[i], sFO, b[i]); sum += y[t][i]; }
@@ -633,12 +663,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
             }
           }
         }
+        stamp(t0);  // 18: outputs written
       }
-      stamp();  // 17 (edge) / 5 (node): outputs written
-      // end of tile: both accumulators and the FFN operand have been fully read by this thread
+      // end of tile: this thread has read everything the tile left in TMEM
       fence_before_sync();
-      mbar_arrive(wk_done);
-      qbase += POST ? 20 : (EDGE ? 30 : 10);
+      mbar_arrive(tile_done);
+      qbase += kChunksTile;
       cx = nx;
     }  // tile loop
   }

@@ -51,7 +51,7 @@ def trace(dev, mode):
     names = ["start", "first operand", "G1 done", "x1 published", "G2 done", "x2 published", "G3 done", "e in TMEM"]
     for j in range(4):
         names += [f"FFN-in {j} done", f"hidden {j} published"]
-    names += ["FFN-out done", "stored"]
+    names += ["next first operand", "FFN-out done", "stored"]
     prev = t[0]
     for i, n in enumerate(names):
         if t[i] == 0:
