@@ -13,6 +13,11 @@
 //   warp 9     weight loader: cp.async.bulk of pre-packed operand images (K-major core-matrix layout, consumption
 //              order, see pack_tc_stream in packppi_b200/weights.py) into a ring; with CLUSTER > 1 every CTA fetches
 //              1/CLUSTER of each image and multicasts it to the whole cluster, dividing the L2 -> SM weight traffic
+//   warp 10    h_E tile loader: one TMA tensor copy (cp.async.bulk.tensor, 128-byte
+//              swizzle) per residue and 32-column chunk brings the tile after the next one into a 64 KB staging
+//              buffer, from which each worker reads its own row without bank conflicts; the edge update writes its
+//              result rows back through the same buffer with TMA stores (a row-per-thread global access would cost
+//              32 L1 wavefronts per instruction, the staged path 4)
 // A chunks are consumed by the MMA warp as soon as they are written, so the epilogue of GEMM n overlaps the MMAs of
 // GEMM n+1.  The FFN input e = LayerNorm(...) is kept in TMEM twice: as packed fp16 (hi, lo) pairs, the TMEM A
 // operand of the four 128-wide slices of the 128 -> 512 Linear, and in fp32 for the residual.
@@ -22,6 +27,8 @@
 // kind::tf32; 1 = hi only (11 bits, the precision of TF32; fast mode, looser tolerance).  Weight images are
 // pre-scaled by a power of two per matrix (weights.py: pack_tc_stream) so that their lo halves stay in the normal
 // fp16 range; the epilogues multiply the accumulator by the inverse scale (exact).
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "common.cuh"
 #include "umma.cuh"
 #include "weights_layout.h"
@@ -33,11 +40,11 @@ using namespace umma;
 
 constexpr int kRows = 128;
 constexpr int kKC = 32;
-constexpr int kSA = 6;   // A ring: slots of 32 k-columns (fp16 hi + lo images, 16 KB)
-constexpr int kSB = 6;   // B ring: slots of one weight chunk (<= 32 k-columns, hi + lo images, 16 KB)
+constexpr int kSA = 4;   // A ring: slots of 32 k-columns (fp16 hi + lo images, 16 KB)
+constexpr int kSB = 4;   // B ring: slots of one weight chunk (<= 32 k-columns, hi + lo images, 16 KB)
 constexpr uint32_t kImgBytes = kRows * kKC * 2;  // one fp16 operand image (hi or lo) of a 32-column chunk: 8 KB
 constexpr uint32_t kSlotBytes = 2 * kImgBytes;   // hi + lo
-constexpr int kThreadsTC = 320;  // 8 worker warps (two groups of 128 rows), MMA warp, loader warp
+constexpr int kThreadsTC = 352;  // 8 worker warps (two groups of 128 rows), MMA warp, weight loader, tile loader
 constexpr uint32_t kLbo = kRows * 16, kSbo = 128;
 constexpr uint32_t kIdesc = idesc_f16(128, 128);
 constexpr int kPairKC = 16;                      // last G1 chunk: 8 pair distances padded to one K = 16 instruction
@@ -48,12 +55,14 @@ constexpr int kChunksEdge = 6 + 4 + 4 + 4 * 8;   // + G3, 4 x (FFN-in slice, FFN
 constexpr long long kImageFloats = 2LL * 128 * (176 + 128 + 128 + 4 * 256) * 2 / 4;
 constexpr long long kStreamFloats = kImageFloats + 8;
 
-constexpr size_t kBarBytes = (2 * kSA + 2 * kSB + 2 + 2) * 8;
+constexpr size_t kBarBytes = (2 * kSA + 2 * kSB + 2 + 2 + 2) * 8;
+constexpr uint32_t kStageBytes = kRows * 128 * 4;  // one tile of h_E rows: 16 boxes (4 chunks x 4 residues) of 4 KB
 // per-column parameters staged in shared memory (floats): b2, b3, LN2 gain/bias, FFN b_in (512), b_out, LN3 gain/bias
 constexpr int kP_B2 = 0, kP_B3 = 128, kP_LN2G = 256, kP_LN2B = 384, kP_BIN = 512, kP_BOUT = 1024, kP_LN3G = 1152,
               kP_LN3B = 1280, kParamFloats = 1408;
 constexpr int kRedFloats = 4 * 2 * 128;  // four row reductions x two groups
-constexpr size_t kSmemTC = ((size_t)kSA + kSB) * kSlotBytes + kBarBytes + 16 + (kParamFloats + kRedFloats) * 4;
+constexpr size_t kSmemTC = kStageBytes + ((size_t)kSA + kSB) * kSlotBytes + kBarBytes + 16 +
+                           (kParamFloats + kRedFloats) * 4;
 
 struct Args {
   const float* geo; const int* nbr; const float* matt;
@@ -88,6 +97,23 @@ __device__ __forceinline__ void bulk_g2s_mc(void* dst, const void* src, uint32_t
       "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
       : "memory");
 }
+// TMA tensor copies of one box {32 floats, K rows, 1 residue} of a [rows][K][128] fp32 tensor (128-byte swizzle)
+__device__ __forceinline__ void tma_load_box(void* dst, const CUtensorMap* tm, int c0, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(0), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_box(const CUtensorMap* tm, int c0, int c2, const void* src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(c0), "r"(0), "r"(c2), "r"(smem_u32(src))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
   asm volatile(
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -126,11 +152,13 @@ __device__ __forceinline__ void ld32(const float* __restrict__ p, float (&d)[32]
 // MODE 1: edge update  (G1, G2, G3, LN, FFN, LN)        tile = 4 residues x 32 edges
 // MODE 2: node epilogue (W3, LN0, FFN, LN1 per residue; reference layers.py:127-132)   tile = 128 residue rows
 template <int MODE, int PASSES, int CLUSTER>
-__global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
+__global__ void __launch_bounds__(kThreadsTC, 1)
+edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out) {
   constexpr bool EDGE = MODE != 0;   // runs the G3 / LayerNorm / FFN part
   constexpr bool POST = MODE == 2;   // per-residue rows instead of per-edge rows, no G1 / G2
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* Aring = smem;
+  uint8_t* stage = smem;  // h_E rows of one tile: box (chunk c, residue rl) at ((c * 4 + rl) << 12), row k at k << 7
+  uint8_t* Aring = stage + kStageBytes;
   uint8_t* Bring = Aring + kSA * kSlotBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(Bring + kSB * kSlotBytes);
   uint64_t* a_full = bars;
@@ -140,8 +168,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
   uint64_t* acc_full = b_empty + kSB;  // [2]
   uint64_t* wk_done = acc_full + 2;     // FFN hand-offs within a tile (e in TMEM, slice j read out)
   uint64_t* tile_done = wk_done + 1;    // the workers have read out everything a tile left in TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_done + 1);
-  float* prm = reinterpret_cast<float*>(tile_done + 3);
+  uint64_t* stage_full = tile_done + 1;  // TMA loads of a tile have landed in the staging buffer
+  uint64_t* stage_free = stage_full + 1; // the staging buffer has been read (by the workers or by the TMA stores)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_free + 1);
+  float* prm = reinterpret_cast<float*>(stage_free + 3);
   float* red = prm + kParamFloats;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -159,6 +189,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
     mbar_init(&acc_full[1], 1);
     mbar_init(wk_done, 256);
     mbar_init(tile_done, 256);
+    mbar_init(stage_full, 1);
+    mbar_init(stage_free, 1);
     mbar_fence_init();
   }
   {  // stage the per-column parameters
@@ -201,6 +233,22 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
           }
           rb_.next(kSB);
           src += 2 * img;
+        }
+      }
+    }
+  } else if (warp == 10) {
+    if (!POST && lane == 0) {
+      // ---------------------------------------------------------------- h_E tile loader (TMA)
+      const uint32_t box_bytes = (uint32_t)min(K, 32) * 128;
+      uint32_t free_phase = 1;  // the buffer starts out free
+      for (int it = 0; it < niter; ++it) {
+        const int r0 = (it * (int)gridDim.x + (int)blockIdx.x) * 4;
+        const int nv = max(0, min(4, R - r0));  // residues of the tile that exist
+        mbar_wait(stage_free, free_phase); free_phase ^= 1;
+        mbar_arrive_expect_tx(stage_full, (uint32_t)nv * 4 * box_bytes);
+        for (int i = 0; i < nv; ++i) {
+          const int row = a.he_shared ? (r0 + i) % a.G : r0 + i;
+          for (int c = 0; c < 4; ++c) tma_load_box(stage + ((c * 4 + i) << 12), &tm_in, c * 32, row, stage_full);
         }
       }
     }
@@ -333,12 +381,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
       return red[(which * 2) * 128 + m] + red[(which * 2 + 1) * 128 + m];
     };
-    auto prefetch_h = [&](const RowCtx& c) {  // pull the next tile's h_E lines into L2 (no registers held)
-      if (c.in_range) {
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(c.hrow + grp * 32));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(c.hrow + (grp + 2) * 32));
-      }
-    };
+    uint32_t sf_phase = 0;
+    // this thread's row in the staging buffer; 16-byte unit u of chunk c sits at (c << 14) + ((u ^ (k & 7)) << 4)
+    uint8_t* const srow = stage + (rl << 12) + (k << 7);
+    const int swz = k & 7;
     // A chunk number q of the kernel-wide schedule -> ring slot q % kSA, (q / kSA)-th use of that slot
     auto publish = [&](int q, const float* vals, int kc) {
       const int slot = q % kSA;
@@ -365,15 +411,31 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
     //      node epilogue: the residue's summed messages scaled by 1/K (the mean over K commutes with W3), 4 chunks.
     //      Edge update: the raw row is also parked in the TMEM region `stash` for the residual, instead of reading
     //      it from global memory a second time (a row-per-thread read costs 32 L1 wavefronts per instruction).
-    auto first_operand = [&](const RowCtx& c, int qb, uint32_t stash) {
+    //      `release`: the staging buffer is handed back to the loader right after the rows have been read (node
+    //      message path, first tile); otherwise the edge update's TMA stores of the previous tile do that.
+    auto first_operand = [&](const RowCtx& c, int qb, uint32_t stash, bool release) {
       float v[32];
       float4 h[2][8];
+      if (POST) {
 #pragma unroll
-      for (int t = 0; t < 2; ++t)
+        for (int t = 0; t < 2; ++t)
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          h[t][u] = c.in_range ? *reinterpret_cast<const float4*>(c.hrow + (grp + 2 * t) * 32 + u * 4)
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int u = 0; u < 8; ++u)
+            h[t][u] = c.in_range ? *reinterpret_cast<const float4*>(c.hrow + (grp + 2 * t) * 32 + u * 4)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        mbar_wait(stage_full, sf_phase); sf_phase ^= 1;
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            h[t][u] = c.in_range ? *reinterpret_cast<const float4*>(srow + ((grp + 2 * t) << 14) + ((u ^ swz) << 4))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (release) {
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (tid == 0) mbar_arrive(stage_free);
+        }
+      }
       if (POST) {
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
@@ -442,7 +504,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
     RowCtx cx = row_ctx(0);
     int qbase = 0;  // first A chunk of the current tile (ring positions persist across tiles)
     stamp(true);  // 0: start
-    first_operand(cx, 0, R0);
+    first_operand(cx, 0, R0, true);
     stamp(true);  // 1: first operand of tile 0 published
 
     for (int it = 0; it < niter; ++it) {
@@ -492,7 +554,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
 
       if (!EDGE) {
         // node message path: the next tile's first operand is built while G2 runs; its G1 then overlaps the reduction
-        if (more) first_operand(nx, qbase + kChunksTile, 0);
+        if (more) first_operand(nx, qbase + kChunksTile, 0, true);
         mbar_wait(&acc_full[1], accph[1]); accph[1] ^= 1;
         fence_after_sync();
         stamp(t0);  // 4: G2 complete
@@ -597,7 +659,6 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
           mbar_arrive(wk_done);
           stamp(t0);  // 7: e in TMEM
         }
-        if (more) prefetch_h(nx);
         // ---- FFN: hidden slice j = relu(acc + b_in[j]) -> the four A chunks of FFN-out slice j
         for (int j = 0; j < 4; ++j) {
           mbar_wait(&acc_full[yb], accph[yb]); accph[yb] ^= 1;
@@ -620,7 +681,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
         }
         // ---- the next tile's first operand is built while FFN-out drains; its head GEMM then overlaps the final
         //      LayerNorm and the stores below.  PK is free: the workers have seen FFN-in 3 complete.
-        if (more) first_operand(nx, qbase + kChunksTile, PK);
+        if (more) first_operand(nx, qbase + kChunksTile, PK, false);
         stamp(t0);  // 16: next first operand published
         // ---- final: y = LN3(e + acc + b_out) * mask   (layers.py:143-146)
         mbar_wait(&acc_full[xb], accph[xb]); accph[xb] ^= 1;
@@ -644,8 +705,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) { float d = y[t][i] - mean3; var += d * d; }
         const float rstd3 = rsqrtf(row_total(var, 3) * (1.f / 128.f) + 1e-5f);
-        float* orow = POST ? a.out + (size_t)rr * 128 : a.out + ((size_t)rr * K + (in_range ? k : 0)) * 128;
-        if (in_range) {
+        // node epilogue: one row per thread straight to global memory; edge update: into the staging buffer (every
+        // worker has read the next tile's rows out of it: the row_total barriers above come after first_operand)
+        float* orow = a.out + (size_t)rr * 128;
+        if (in_range || !POST) {
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             const int c = grp + 2 * t;
@@ -659,8 +722,22 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
               o.y = on ? (y[t][i + 1] - mean3) * rstd3 * gm[i + 1] + bt[i + 1] : 0.f;
               o.z = on ? (y[t][i + 2] - mean3) * rstd3 * gm[i + 2] + bt[i + 2] : 0.f;
               o.w = on ? (y[t][i + 3] - mean3) * rstd3 * gm[i + 3] + bt[i + 3] : 0.f;
-              *reinterpret_cast<float4*>(orow + c * 32 + i) = o;
+              if (POST) *reinterpret_cast<float4*>(orow + c * 32 + i) = o;
+              else *reinterpret_cast<float4*>(srow + (c << 14) + ((u ^ swz) << 4)) = o;
             }
+          }
+        }
+        if (!POST) {
+          fence_async_smem();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (tid == 0) {  // rows k >= K and residues past the end are clipped by the tensor map / skipped here
+            const int r0 = (it * (int)gridDim.x + (int)blockIdx.x) * 4;
+            const int nv = max(0, min(4, R - r0));
+            for (int i = 0; i < nv; ++i)
+              for (int c = 0; c < 4; ++c) tma_store_box(&tm_out, c * 32, r0 + i, stage + ((c * 4 + i) << 12));
+            bulk_commit();
+            bulk_wait_read();
+            mbar_arrive(stage_free);
           }
         }
         stamp(t0);  // 18: outputs written
@@ -671,6 +748,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
       qbase += kChunksTile;
       cx = nx;
     }  // tile loop
+    if (MODE == 1 && tid == 0) bulk_wait_all();  // the result rows are in global memory before the CTA retires
   }
 
   // ---- teardown: all tensor-core work of this CTA has been consumed by its workers; in a cluster nobody may exit
@@ -679,6 +757,36 @@ __global__ void __launch_bounds__(kThreadsTC, 1) edge_tc_kernel(const Args a) {
   __syncthreads();
   if (CLUSTER > 1) cluster_sync_all();
   if (warp == 8) tmem_dealloc<512>(tmem);
+}
+
+// Tensor map of a [rows][K][128] fp32 tensor with boxes {32 floats, min(K, 32) rows, 1}: one residue's rows of one
+// 32-column chunk, 128-byte swizzle (16-byte unit u of row k lands at k * 128 + ((u ^ (k & 7)) << 4))
+static int make_row_map(CUtensorMap* tm, const float* base, long long rows, int K) {
+  using Encode = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static Encode encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+      snprintf(g_last_error, sizeof(g_last_error), "edge_tc_kernel: cuTensorMapEncodeTiled is not available");
+      return 1;
+    }
+    encode = reinterpret_cast<Encode>(fn);
+  }
+  const cuuint64_t gdim[3] = {128, (cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t gstr[2] = {512, (cuuint64_t)K * 512};
+  const cuuint32_t box[3] = {32, (cuuint32_t)(K < 32 ? K : 32), 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult rc = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    snprintf(g_last_error, sizeof(g_last_error), "edge_tc_kernel: cuTensorMapEncodeTiled failed (%d)", (int)rc);
+    return 1;
+  }
+  return 0;
 }
 
 template <int MODE, int PASSES, int CLUSTER>
@@ -690,6 +798,11 @@ static int launch(const Args& a, cudaStream_t stream) {
     return 1;
   }
   const long long R = (long long)a.S * a.G;
+  alignas(64) CUtensorMap tm_in, tm_out;
+  memset(&tm_in, 0, sizeof(tm_in));
+  memset(&tm_out, 0, sizeof(tm_out));
+  if (MODE != 2 && make_row_map(&tm_in, a.hE_in, a.he_shared ? a.G : R, a.K)) return 1;
+  if (MODE == 1 && make_row_map(&tm_out, a.out, R, a.K)) return 1;
   unsigned tiles = (MODE == 2) ? (unsigned)((R + kRows - 1) / kRows) : (unsigned)((R + 3) / 4);
   static int num_sms = 0;
   if (num_sms == 0) {
@@ -712,7 +825,7 @@ static int launch(const Args& a, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, kern, a);
+  e = cudaLaunchKernelEx(&cfg, kern, a, tm_in, tm_out);
   if (e != cudaSuccess) {
     snprintf(g_last_error, sizeof(g_last_error), "edge_tc_kernel: launch: %s", cudaGetErrorString(e));
     return 1;
