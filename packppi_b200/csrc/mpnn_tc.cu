@@ -40,8 +40,14 @@ using namespace umma;
 
 constexpr int kRows = 128;
 constexpr int kKC = 32;
-constexpr int kSA = 4;   // A ring: slots of 32 k-columns (fp16 hi + lo images, 16 KB)
-constexpr int kSB = 4;   // B ring: slots of one weight chunk (<= 32 k-columns, hi + lo images, 16 KB)
+#ifndef PP_TC_SA
+#define PP_TC_SA 4
+#endif
+#ifndef PP_TC_SB
+#define PP_TC_SB 4
+#endif
+constexpr int kSA = PP_TC_SA;   // A ring: slots of 32 k-columns (fp16 hi + lo images, 16 KB)
+constexpr int kSB = PP_TC_SB;   // B ring: slots of one weight chunk (<= 32 k-columns, hi + lo images, 16 KB)
 constexpr uint32_t kImgBytes = kRows * kKC * 2;  // one fp16 operand image (hi or lo) of a 32-column chunk: 8 KB
 constexpr uint32_t kSlotBytes = 2 * kImgBytes;   // hi + lo
 constexpr int kThreadsTC = 352;  // 8 worker warps (two groups of 128 rows), MMA warp, weight loader, tile loader
@@ -169,7 +175,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
   uint64_t* wk_done = acc_full + 2;     // FFN hand-offs within a tile (e in TMEM, slice j read out)
   uint64_t* tile_done = wk_done + 1;    // the workers have read out everything a tile left in TMEM
   uint64_t* stage_full = tile_done + 1;  // TMA loads of a tile have landed in the staging buffer
-  uint64_t* stage_free = stage_full + 1; // the staging buffer has been read (by the workers or by the TMA stores)
+  uint64_t* stage_free = stage_full + 1; // the workers are done with the staging buffer: rows read / result rows written
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_free + 1);
   float* prm = reinterpret_cast<float*>(stage_free + 3);
   float* red = prm + kParamFloats;
@@ -190,7 +196,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
     mbar_init(wk_done, 256);
     mbar_init(tile_done, 256);
     mbar_init(stage_full, 1);
-    mbar_init(stage_free, 1);
+    mbar_init(stage_free, 256);
     mbar_fence_init();
   }
   {  // stage the per-column parameters
@@ -239,17 +245,38 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
   } else if (warp == 10) {
     if (!POST && lane == 0) {
       // ---------------------------------------------------------------- h_E tile loader (TMA)
+      // This thread owns the staging buffer.  Node message path: tile t+1 is fetched as soon as the workers have
+      // read tile t.  Edge update: the workers read tile it+1, then write the result rows of tile it into the buffer;
+      // those are stored from here and tile it+2 is fetched once the stores have read the buffer.
       const uint32_t box_bytes = (uint32_t)min(K, 32) * 128;
-      uint32_t free_phase = 1;  // the buffer starts out free
-      for (int it = 0; it < niter; ++it) {
-        const int r0 = (it * (int)gridDim.x + (int)blockIdx.x) * 4;
+      uint32_t free_phase = 0;
+      auto first_row = [&](int it) { return (it * (int)gridDim.x + (int)blockIdx.x) * 4; };
+      auto load_tile = [&](int it) {
+        const int r0 = first_row(it);
         const int nv = max(0, min(4, R - r0));  // residues of the tile that exist
-        mbar_wait(stage_free, free_phase); free_phase ^= 1;
         mbar_arrive_expect_tx(stage_full, (uint32_t)nv * 4 * box_bytes);
         for (int i = 0; i < nv; ++i) {
           const int row = a.he_shared ? (r0 + i) % a.G : r0 + i;
           for (int c = 0; c < 4; ++c) tma_load_box(stage + ((c * 4 + i) << 12), &tm_in, c * 32, row, stage_full);
         }
+      };
+      auto wait_workers = [&]() { mbar_wait(stage_free, free_phase); free_phase ^= 1; };
+      load_tile(0);
+      if (MODE == 0) {
+        for (int it = 1; it < niter; ++it) { wait_workers(); load_tile(it); }
+      } else {
+        wait_workers();  // tile 0 has been read
+        if (niter > 1) load_tile(1);
+        for (int it = 0; it < niter; ++it) {
+          wait_workers();  // result rows of tile `it` are in the buffer (and tile it+1 has been read out of it)
+          const int r0 = first_row(it);
+          const int nv = max(0, min(4, R - r0));  // rows k >= K are clipped by the tensor map
+          for (int i = 0; i < nv; ++i)
+            for (int c = 0; c < 4; ++c) tma_store_box(&tm_out, c * 32, r0 + i, stage + ((c * 4 + i) << 12));
+          bulk_commit();
+          if (it + 2 < niter) { bulk_wait_read(); load_tile(it + 2); }
+        }
+        bulk_wait_all();  // the result rows are in global memory before the CTA retires
       }
     }
   } else if (warp == 8) {
@@ -431,10 +458,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
           for (int u = 0; u < 8; ++u)
             h[t][u] = c.in_range ? *reinterpret_cast<const float4*>(srow + ((grp + 2 * t) << 14) + ((u ^ swz) << 4))
                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (release) {
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (tid == 0) mbar_arrive(stage_free);
-        }
+        if (release) mbar_arrive(stage_free);
       }
       if (POST) {
 #pragma unroll
@@ -664,17 +688,19 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
           mbar_wait(&acc_full[yb], accph[yb]); accph[yb] ^= 1;
           fence_after_sync();
           stamp(t0);  // 8 + 2j: FFN-in slice j complete
+          float v2[32];
+          load_acc(Y, grp, v);
+          load_acc(Y, grp + 2, v2);
+          // Y is drained for this thread: the next FFN-in slice / the next tile's head may overwrite it.  Signalled
+          // before the chunks are published, which can block on a ring slot that only FFN-out j-1 frees.
+          fence_before_sync();
+          mbar_arrive(wk_done);
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             const int c = grp + 2 * t;
-            load_acc(Y, c, v);
-            if (t == 1) {  // Y is drained for this thread: the next FFN-in slice / the next tile's head may overwrite it
-              fence_before_sync();
-              mbar_arrive(wk_done);
-            }
             const float* b = prm + kP_BIN + j * 128 + c * 32;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(fmaf(v[i], sFI, b[i]), 0.f);
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(fmaf(t ? v2[i] : v[i], sFI, b[i]), 0.f);
             publish(qbase + (POST ? 4 : 14) + 4 * j + c, v, kKC);
           }
           stamp(t0);  // 9 + 2j: hidden slice j published
@@ -727,18 +753,9 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
             }
           }
         }
-        if (!POST) {
+        if (!POST) {  // hand the rows to the tile loader's TMA stores
           fence_async_smem();
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (tid == 0) {  // rows k >= K and residues past the end are clipped by the tensor map / skipped here
-            const int r0 = (it * (int)gridDim.x + (int)blockIdx.x) * 4;
-            const int nv = max(0, min(4, R - r0));
-            for (int i = 0; i < nv; ++i)
-              for (int c = 0; c < 4; ++c) tma_store_box(&tm_out, c * 32, r0 + i, stage + ((c * 4 + i) << 12));
-            bulk_commit();
-            bulk_wait_read();
-            mbar_arrive(stage_free);
-          }
+          mbar_arrive(stage_free);
         }
         stamp(t0);  // 18: outputs written
       }
@@ -748,7 +765,6 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
       qbase += kChunksTile;
       cx = nx;
     }  // tile loop
-    if (MODE == 1 && tid == 0) bulk_wait_all();  // the result rows are in global memory before the CTA retires
   }
 
   // ---- teardown: all tensor-core work of this CTA has been consumed by its workers; in a cluster nobody may exit
