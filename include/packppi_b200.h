@@ -97,13 +97,16 @@ int pp_ipmp_edge_edge(const float* weights, int64_t layer, const float* geo, con
 
 /* Tensor-core (tcgen05 / TMEM) version of pp_ipmp_edge_node (path 0) and pp_ipmp_edge_edge (path 1): same inputs,
  * same outputs.  wstream = operand images of this layer and path (pp_tc_stream_floats() floats, built by
- * packppi_b200.weights.pack_tc_stream).  passes 3 = split TF32 (fp32-grade), 1 = plain TF32; cluster = 1, 2 or 4
- * CTAs that share (multicast) the weight stream.  out = accsum [S*G][128] or hE_out [S*G][K][128]. */
+ * packppi_b200.weights.pack_tc_stream: fp16 (hi, lo) image pairs, kind::f16 MMAs).  passes 3 = split fp16
+ * (fp32-grade), 1 = plain fp16 inputs; cluster = 1, 2 or 4 CTAs that share (multicast) the weight stream.
+ * msum [G] = mean of mask_attend over K (pp_knn_build): tiles whose residues all have msum == 0 (padding) are
+ * skipped and their outputs zeroed (cluster == 1).  out = accsum [S*G][128] or hE_out [S*G][K][128]; hE_in / hE_out
+ * move through TMA tensor copies and must be 16-byte aligned. */
 int64_t pp_tc_stream_floats(void);
 int pp_ipmp_edge_tc(const float* weights, int64_t layer, int64_t path, const float* wstream, const float* geo,
-                    const int32_t* nbr, const float* mask_attend, int64_t G, int64_t K, int64_t S,
-                    const float* hE_in, int64_t he_shared, const float* wsA, const float* wsN, const float* wsP,
-                    float* out, int64_t passes, int64_t cluster, pp_stream_t stream);
+                    const int32_t* nbr, const float* mask_attend, const float* msum, int64_t G, int64_t K,
+                    int64_t S, const float* hE_in, int64_t he_shared, const float* wsA, const float* wsN,
+                    const float* wsP, float* out, int64_t passes, int64_t cluster, pp_stream_t stream);
 
 /* Tensor-core version of pp_ipmp_node_post (reference layers.py:127-132), same kernel family: tile = 128 residue
  * rows.  wstream = operand images of path 2 of this layer; hV [S*G][128] is updated in place. */

@@ -26,7 +26,7 @@ SIGNATURES = {
     "pp_ipmp_edge_node": "p" "i" "pppp" "iii" "p" "i" "pppp" "s",
     "pp_ipmp_node_post": "p" "i" "ppppp" "iii" "pp" "s",
     "pp_ipmp_edge_edge": "p" "i" "pppp" "iii" "p" "i" "pppp" "s",
-    "pp_ipmp_edge_tc": "p" "ii" "pppp" "iii" "p" "i" "pppp" "ii" "s",
+    "pp_ipmp_edge_tc": "p" "ii" "ppppp" "iii" "p" "i" "pppp" "ii" "s",
     "pp_ipmp_node_post_tc": "p" "i" "ppp" "iii" "pp" "ii" "s",
     "pp_decode_step": "pp" "ii" "p" "i" "ff" "ppp" "ppp" "f" "s",
     "pp_atom14_fwd": "pppp" "ii" "p" "s",

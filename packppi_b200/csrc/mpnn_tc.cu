@@ -77,7 +77,8 @@ struct Args {
   const float *B2, *B3, *LNG, *LNB, *BIN, *BOUT, *LN3G, *LN3B;
   const float* hE_in; int he_shared;
   const float *A, *Nn, *pglob;
-  const float *rmask, *msum, *hres;  // MODE 2: residue mask [G], mean attention mask [G], residual rows h_V [R][128]
+  const float* msum;                 // mean attention mask [G]: 0 marks a padding residue (MODE 2: scales b3)
+  const float *rmask, *hres;         // MODE 2: residue mask [G], residual rows h_V [R][128]
   float in_scale;                    // MODE 2: 1 / K applied to the summed messages
   float* out;             // node path: accsum [R][128]; edge path: hE_out [R][K][128]
   unsigned long long* trace;  // optional: clock64 stamps of CTA 0 / first tile (pp_set_tc_trace), else null
@@ -187,6 +188,24 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
   // iterations past the last tile work on fully masked rows
   const int niter = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
   constexpr uint16_t kMask = (uint16_t)((1u << CLUSTER) - 1);
+  // A CTA that owns its weight stream skips tiles whose four residues are all padding (mean attention mask 0): every
+  // role walks the same sequence of live tiles, the workers zero the outputs of the ones they pass over.
+  constexpr bool SKIP = CLUSTER == 1 && !POST;
+  const int tstep = (int)gridDim.x;
+  const int tend = SKIP ? ntiles : niter * tstep;  // tiles of this CTA: blockIdx.x, + tstep, ... < tend
+  auto live = [&](int tile) {
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = tile * 4 + i;
+      if (r < R) any |= a.msum[r % a.G] != 0.f;
+    }
+    return any;
+  };
+  auto next_tile = [&](int tile) {
+    if (SKIP) while (tile < tend && !live(tile)) tile += tstep;
+    return tile;
+  };
 
   if (tid == 0) {
     for (int i = 0; i < kSA; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
@@ -221,7 +240,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
     if (lane == 0) {
       Ring rb_{0, 1};
       const uint32_t crank = (CLUSTER > 1) ? cluster_rank() : 0;
-      for (int it = 0; it < niter; ++it) {
+      for (int tile = next_tile((int)blockIdx.x); tile < tend; tile = next_tile(tile + tstep)) {
         const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wstream);
         constexpr int NCHUNK = POST ? 36 : (EDGE ? kChunksEdge : kChunksNode);
         for (int i = 0; i < NCHUNK; ++i) {
@@ -250,9 +269,8 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
       // those are stored from here and tile it+2 is fetched once the stores have read the buffer.
       const uint32_t box_bytes = (uint32_t)min(K, 32) * 128;
       uint32_t free_phase = 0;
-      auto first_row = [&](int it) { return (it * (int)gridDim.x + (int)blockIdx.x) * 4; };
-      auto load_tile = [&](int it) {
-        const int r0 = first_row(it);
+      auto load_tile = [&](int tile) {
+        const int r0 = tile * 4;
         const int nv = max(0, min(4, R - r0));  // residues of the tile that exist
         mbar_arrive_expect_tx(stage_full, (uint32_t)nv * 4 * box_bytes);
         for (int i = 0; i < nv; ++i) {
@@ -261,22 +279,29 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
         }
       };
       auto wait_workers = [&]() { mbar_wait(stage_free, free_phase); free_phase ^= 1; };
-      load_tile(0);
-      if (MODE == 0) {
-        for (int it = 1; it < niter; ++it) { wait_workers(); load_tile(it); }
-      } else {
-        wait_workers();  // tile 0 has been read
-        if (niter > 1) load_tile(1);
-        for (int it = 0; it < niter; ++it) {
-          wait_workers();  // result rows of tile `it` are in the buffer (and tile it+1 has been read out of it)
-          const int r0 = first_row(it);
-          const int nv = max(0, min(4, R - r0));  // rows k >= K are clipped by the tensor map
-          for (int i = 0; i < nv; ++i)
-            for (int c = 0; c < 4; ++c) tma_store_box(&tm_out, c * 32, r0 + i, stage + ((c * 4 + i) << 12));
-          bulk_commit();
-          if (it + 2 < niter) { bulk_wait_read(); load_tile(it + 2); }
+      int cur = next_tile((int)blockIdx.x);
+      if (cur < tend) {
+        load_tile(cur);
+        if (MODE == 0) {
+          for (int t = next_tile(cur + tstep); t < tend; t = next_tile(t + tstep)) { wait_workers(); load_tile(t); }
+        } else {
+          wait_workers();  // the first tile has been read
+          int nxt = next_tile(cur + tstep);
+          if (nxt < tend) load_tile(nxt);
+          while (cur < tend) {
+            wait_workers();  // result rows of tile `cur` are in the buffer (and tile `nxt` has been read out of it)
+            const int r0 = cur * 4;
+            const int nv = max(0, min(4, R - r0));  // rows k >= K are clipped by the tensor map
+            for (int i = 0; i < nv; ++i)
+              for (int c = 0; c < 4; ++c) tma_store_box(&tm_out, c * 32, r0 + i, stage + ((c * 4 + i) << 12));
+            bulk_commit();
+            const int after = nxt < tend ? next_tile(nxt + tstep) : tend;
+            if (after < tend) { bulk_wait_read(); load_tile(after); }
+            cur = nxt;
+            nxt = after;
+          }
+          bulk_wait_all();  // the result rows are in global memory before the CTA retires
         }
-        bulk_wait_all();  // the result rows are in global memory before the CTA retires
       }
     }
   } else if (warp == 8) {
@@ -317,8 +342,12 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
       // Tiles are software-pipelined: the head GEMM of tile it+1 is issued before the workers run the last epilogue of
       // tile it.  In the EDGE modes the roles of the two accumulators (X: head, G3, FFN-out; Y: G2, FFN-in) and of
       // the two TMEM operand regions swap with the parity of the tile so that nothing live is overwritten.
-      head(ACC0, 0);
-      for (int it = 0; it < niter; ++it) {
+      int tile = next_tile((int)blockIdx.x);
+      if (tile < tend) head(ACC0, 0);
+      for (int it = 0; tile < tend; ++it) {
+        const int nxt_tile = next_tile(tile + tstep);
+        const bool more = nxt_tile < tend;
+        tile = nxt_tile;
         const int par = EDGE ? (it & 1) : 0;
         const uint32_t X = par ? ACC1 : ACC0, Y = par ? ACC0 : ACC1;
         const int xb = par, yb = par ^ 1;
@@ -332,7 +361,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
         }
         if (!EDGE) {
           // G2's operand chunks exist only once every worker has drained ACC0, so the next G1 may follow directly
-          if (it + 1 < niter) head(ACC0, 0);
+          if (more) head(ACC0, 0);
           continue;
         }
         if (!POST) {
@@ -353,7 +382,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
           for (int c = 0; c < 4; ++c) chunk(true, X, 0, kKC, j == 0 && c == 0);  // FFN-out slice j accumulates
         }
         mma_commit(&acc_full[xb]);
-        if (it + 1 < niter) {
+        if (more) {
           wait_workers();  // slice 3 has been read out of Y, which becomes the X of the next tile
           head(Y, yb);
         }
@@ -380,9 +409,8 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
       bool in_range, on;
       const float* hrow;
     };
-    auto row_ctx = [&](int it) {
+    auto row_ctx = [&](int tile) {
       RowCtx c;
-      const int tile = it * (int)gridDim.x + (int)blockIdx.x;
       if (POST) {  // one residue row per thread
         c.r = tile * kRows + m;
         c.in_range = c.r < R;
@@ -525,14 +553,30 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
       if (grp == 0) publish(qb + 4, geo, kKC); else publish(qb + 5, geo, kPairKC);
     };
 
-    RowCtx cx = row_ctx(0);
+    // the outputs of the padding tiles this CTA passes over: zeros, written with plain coalesced stores
+    auto next_tile_zeroing = [&](int tile) {
+      if (SKIP) {
+        while (tile < tend && !live(tile)) {
+          const int r0 = tile * 4;
+          const int nrow = max(0, min(4, R - r0)) * (EDGE ? K : 1);  // rows of 128 floats
+          float4* dst = reinterpret_cast<float4*>(a.out + (size_t)r0 * (EDGE ? K : 1) * 128);
+          for (int i = tid; i < nrow * 32; i += 256) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          tile += tstep;
+        }
+      }
+      return tile;
+    };
+    int tile = next_tile_zeroing((int)blockIdx.x);
+    RowCtx cx = row_ctx(tile);
     int qbase = 0;  // first A chunk of the current tile (ring positions persist across tiles)
     stamp(true);  // 0: start
-    first_operand(cx, 0, R0, true);
-    stamp(true);  // 1: first operand of tile 0 published
+    if (tile < tend) first_operand(cx, 0, R0, true);
+    stamp(true);  // 1: first operand of the first tile published
 
-    for (int it = 0; it < niter; ++it) {
+    for (int it = 0; tile < tend; ++it) {
       const bool t0 = it == 0;
+      const int nxt_tile = next_tile_zeroing(tile + tstep);
+      const bool more = nxt_tile < tend;
       const int par = EDGE ? (it & 1) : 0;
       const uint32_t X = par ? ACC1 : ACC0, Y = par ? ACC0 : ACC1;
       const int xb = par, yb = par ^ 1;
@@ -540,9 +584,8 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
       const uint32_t PK = par ? R0 : R1;   // e as packed fp16: hi in columns [0, 64), lo in [64, 128)
       const bool on = cx.on, in_range = cx.in_range;
       const int r = cx.r, rr = cx.rr;
-      const bool more = it + 1 < niter;
       RowCtx nx = cx;
-      if (more) nx = row_ctx(it + 1);
+      if (more) nx = row_ctx(nxt_tile);
       float v[32];
 
       // ---- epilogue of the head GEMM G1: x1 = relu(acc + A_i + N_j); the two gathered rows are fetched before the wait
@@ -764,6 +807,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
       mbar_arrive(tile_done);
       qbase += kChunksTile;
       cx = nx;
+      tile = nxt_tile;
     }  // tile loop
   }
 
@@ -869,17 +913,18 @@ extern "C" int pp_set_tc_trace(uint64_t* trace) {
 //   passes : 3 = split fp16 (fp32-grade), 1 = plain fp16 inputs;  cluster: 1, 2 or 4 CTAs sharing the weight stream
 //   out    : accsum [S*G][128] (path 0) or hE_out [S*G][K][128] (path 1, may alias hE_in when he_shared == 0)
 extern "C" int pp_ipmp_edge_tc(const float* weights, int64_t layer, int64_t path, const float* wstream,
-                               const float* geo, const int32_t* nbr, const float* mask_attend, int64_t G, int64_t K,
-                               int64_t S, const float* hE_in, int64_t he_shared, const float* wsA, const float* wsN,
+                               const float* geo, const int32_t* nbr, const float* mask_attend, const float* msum,
+                               int64_t G, int64_t K, int64_t S, const float* hE_in, int64_t he_shared, const float* wsA, const float* wsN,
                                const float* wsP, float* out, int64_t passes, int64_t cluster, cudaStream_t stream) {
-  PP_REQUIRE(weights && wstream && geo && nbr && mask_attend && hE_in && wsA && wsN && wsP && out, "null pointer");
+  PP_REQUIRE(weights && wstream && geo && nbr && mask_attend && msum && hE_in && wsA && wsN && wsP && out,
+             "null pointer");
   PP_REQUIRE(layer >= 0 && layer < 3 && (path == 0 || path == 1), "layer / path out of range");
   PP_REQUIRE(G > 0 && S > 0 && K > 0 && K <= PP_KMAX, "bad sizes");
   PP_REQUIRE(passes == 1 || passes == 3, "passes must be 1 or 3");
   PP_REQUIRE(cluster == 1 || cluster == 2 || cluster == 4, "cluster must be 1, 2 or 4");
   const float* Lb = weights + layer * wl::kLayerStride;
   tc::Args a{};
-  a.geo = geo; a.nbr = nbr; a.matt = mask_attend;
+  a.geo = geo; a.nbr = nbr; a.matt = mask_attend; a.msum = msum;
   a.G = (int)G; a.K = (int)K; a.S = (int)S;
   a.wstream = wstream;
   a.B2 = Lb + (path ? PP_OFF(L0_E_B2) : PP_OFF(L0_N_B2));

@@ -202,7 +202,7 @@ class Engine:
                 _lib.call("pp_ipmp_edge_node", W, layer, *common, *size, hE_in, shared, ws.wsA, ws.wsN, ws.wsP,
                           ws.wsAcc, rows=S * G)
             else:
-                _lib.call("pp_ipmp_edge_tc", W, layer, 0, self.wtc[layer, 0], *common, G, K, S, hE_in, shared, ws.wsA,
+                _lib.call("pp_ipmp_edge_tc", W, layer, 0, self.wtc[layer, 0], *common, graph.msum, G, K, S, hE_in, shared, ws.wsA,
                           ws.wsN, ws.wsP, ws.wsAcc, *tcp, rows=S * G, tag="node")
             if self.mode == "fp32" or self.node_epilogue == "ffma":
                 _lib.call("pp_ipmp_node_post", W, layer, *common, graph.msum, *size, ws.wsAcc, ws.hV, rows=S * G)
@@ -217,7 +217,7 @@ class Engine:
                     _lib.call("pp_ipmp_edge_edge", W, layer, *common, *size, hE_in, shared, ws.wsA, ws.wsN, ws.wsP,
                               ws.hE, rows=S * G)
                 else:
-                    _lib.call("pp_ipmp_edge_tc", W, layer, 1, self.wtc[layer, 1], *common, G, K, S, hE_in, shared,
+                    _lib.call("pp_ipmp_edge_tc", W, layer, 1, self.wtc[layer, 1], *common, graph.msum, G, K, S, hE_in, shared,
                               ws.wsA, ws.wsN, ws.wsP, ws.hE, *tcp, rows=S * G, tag="edge")
         return ws.hV
 

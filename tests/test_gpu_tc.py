@@ -49,3 +49,37 @@ def test_sampling_tc(case, mode, cluster):
     d = wrapped_diff(out.cpu(), tt(g["ref_SC_D_final"]))
     print(f"{case} {mode} cluster={cluster}: max chi diff {d.max().item():.3e} rad, mean {d.mean().item():.3e}")
     assert d.max().item() < TOL[mode]["chi"]
+
+
+def test_padding_tiles_are_skipped_and_zeroed():
+    """A batch padded to its longest complex: the tensor-core kernels skip the tiles that hold only padding residues
+    and must still leave zeros there (the buffers are poisoned first), identical to the CUDA-core kernels elsewhere."""
+    from packppi_b200 import TDiffusionModule, weights, synthetic, _lib
+    from packppi_b200.batch import collate
+    dev = torch.device("cuda:0")
+    batch = collate([synthetic.make_complex((20, 21), seed=1), synthetic.make_complex((90, 83), seed=2),
+                     synthetic.make_complex((30, 30), seed=3)]).to(dev)
+    B, L = batch.X.shape[:2]
+    chi = (torch.rand(2, B, L, 4, generator=torch.Generator().manual_seed(5)) * 6.0 - 3.0).to(dev)
+    outs = {}
+    for mode in ("fp32", "f16x3"):
+        m = TDiffusionModule()
+        m.load_state_dict(weights.make_state_dict(0))
+        m.kernel_mode = mode
+        m = m.to(dev).eval()
+        eng, graph = m._graph(batch)
+        ws = eng.workspace(graph.G, graph.K, 2)
+        for buf in (ws.hE, ws.hV, ws.wsAcc):
+            buf.fill_(float("nan"))
+        ni = eng.node_inputs(batch)
+        t = torch.full((2 * B * L,), 0.4, device=dev)
+        eng.forward_layers(graph, ws, ni, chi.reshape(-1, 4).contiguous(), t, 1)
+        torch.cuda.synchronize()
+        outs[mode] = (ws.hV.clone(), ws.hE.clone())
+    pad = (batch.residue_mask.reshape(-1) == 0).repeat(2)
+    assert int(pad.sum()) >= 2 * 200
+    for mode, (hV, hE) in outs.items():
+        assert torch.isfinite(hV).all() and torch.isfinite(hE).all(), mode
+        assert hV[pad].abs().max().item() == 0.0 and hE.reshape(hV.shape[0], -1)[pad].abs().max().item() == 0.0, mode
+    assert (outs["fp32"][0] - outs["f16x3"][0]).abs().max().item() < TOL["f16x3"]["act"]
+    assert (outs["fp32"][1] - outs["f16x3"][1]).abs().max().item() < TOL["f16x3"]["act"]
