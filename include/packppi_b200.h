@@ -100,7 +100,8 @@ int pp_ipmp_edge_edge(const float* weights, int64_t layer, const float* geo, con
  * packppi_b200.weights.pack_tc_stream: fp16 (hi, lo) image pairs, kind::f16 MMAs).  passes 3 = split fp16
  * (fp32-grade), 1 = plain fp16 inputs; cluster = 1, 2 or 4 CTAs that share (multicast) the weight stream.
  * msum [G] = mean of mask_attend over K (pp_knn_build): tiles whose residues all have msum == 0 (padding) are
- * skipped and their outputs zeroed (cluster == 1).  out = accsum [S*G][128] or hE_out [S*G][K][128]; hE_in / hE_out
+ * skipped and their output rows left untouched (cluster == 1; zero the buffers once, the kernels of this library
+ * never write anything else there).  out = accsum [S*G][128] or hE_out [S*G][K][128]; hE_in / hE_out
  * move through TMA tensor copies and must be 16-byte aligned. */
 int64_t pp_tc_stream_floats(void);
 int pp_ipmp_edge_tc(const float* weights, int64_t layer, int64_t path, const float* wstream, const float* geo,

@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpackppi_b200.so")
+LIB_PATH = os.environ.get("PACKPPI_B200_LIB") or os.path.join(_HERE, "csrc", "libpackppi_b200.so")  # override: A/B builds
 
 _P, _I, _F = ctypes.c_void_p, ctypes.c_int64, ctypes.c_float
 

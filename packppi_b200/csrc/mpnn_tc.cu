@@ -189,8 +189,12 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
   const int niter = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
   constexpr uint16_t kMask = (uint16_t)((1u << CLUSTER) - 1);
   // A CTA that owns its weight stream skips tiles whose four residues are all padding (mean attention mask 0): every
-  // role walks the same sequence of live tiles, the workers zero the outputs of the ones they pass over.
-  constexpr bool SKIP = CLUSTER == 1 && !POST;
+  // role walks the same sequence of live tiles.  The output rows of skipped tiles are not written: the caller keeps
+  // them zero (nothing but the skipped tiles themselves ever reads or writes them).
+#ifndef PP_TC_SKIP
+#define PP_TC_SKIP 1
+#endif
+  constexpr bool SKIP = PP_TC_SKIP && CLUSTER == 1 && !POST;
   const int tstep = (int)gridDim.x;
   const int tend = SKIP ? ntiles : niter * tstep;  // tiles of this CTA: blockIdx.x, + tstep, ... < tend
   auto live = [&](int tile) {
@@ -296,7 +300,12 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
               for (int c = 0; c < 4; ++c) tma_store_box(&tm_out, c * 32, r0 + i, stage + ((c * 4 + i) << 12));
             bulk_commit();
             const int after = nxt < tend ? next_tile(nxt + tstep) : tend;
+#ifdef PP_TC_ALWAYS_WAIT_READ
+            bulk_wait_read();
+            if (after < tend) load_tile(after);
+#else
             if (after < tend) { bulk_wait_read(); load_tile(after); }
+#endif
             cur = nxt;
             nxt = after;
           }
@@ -466,8 +475,8 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
     //      node epilogue: the residue's summed messages scaled by 1/K (the mean over K commutes with W3), 4 chunks.
     //      Edge update: the raw row is also parked in the TMEM region `stash` for the residual, instead of reading
     //      it from global memory a second time (a row-per-thread read costs 32 L1 wavefronts per instruction).
-    //      `release`: the staging buffer is handed back to the loader right after the rows have been read (node
-    //      message path, first tile); otherwise the edge update's TMA stores of the previous tile do that.
+    //      `release`: the staging buffer is handed back to the loader once the rows have been consumed (node message
+    //      path, first tile); otherwise the edge update's result rows of the previous tile do that.
     auto first_operand = [&](const RowCtx& c, int qb, uint32_t stash, bool release) {
       float v[32];
       float4 h[2][8];
@@ -486,7 +495,6 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
           for (int u = 0; u < 8; ++u)
             h[t][u] = c.in_range ? *reinterpret_cast<const float4*>(srow + ((grp + 2 * t) << 14) + ((u ^ swz) << 4))
                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (release) mbar_arrive(stage_free);
       }
       if (POST) {
 #pragma unroll
@@ -531,6 +539,10 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
         if (MODE == 1) store_tmem(stash + (grp + 2 * t) * 32, v);
         publish(qb + grp + 2 * t, v, kKC);
       }
+      // Hand the buffer back only now: the rows have provably left shared memory (their values were consumed by the
+      // stores above).  Arriving right after issuing the loads let the next TMA copy overtake reads still in flight
+      // (measured: one corrupted residue in ~1000 tiles when the copy hits in L2).
+      if (release) mbar_arrive(stage_free);
       if (MODE == 1) tmem_st_wait();
       float geo[32];
 #pragma unroll
@@ -553,20 +565,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
       if (grp == 0) publish(qb + 4, geo, kKC); else publish(qb + 5, geo, kPairKC);
     };
 
-    // the outputs of the padding tiles this CTA passes over: zeros, written with plain coalesced stores
-    auto next_tile_zeroing = [&](int tile) {
-      if (SKIP) {
-        while (tile < tend && !live(tile)) {
-          const int r0 = tile * 4;
-          const int nrow = max(0, min(4, R - r0)) * (EDGE ? K : 1);  // rows of 128 floats
-          float4* dst = reinterpret_cast<float4*>(a.out + (size_t)r0 * (EDGE ? K : 1) * 128);
-          for (int i = tid; i < nrow * 32; i += 256) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          tile += tstep;
-        }
-      }
-      return tile;
-    };
-    int tile = next_tile_zeroing((int)blockIdx.x);
+    int tile = next_tile((int)blockIdx.x);
     RowCtx cx = row_ctx(tile);
     int qbase = 0;  // first A chunk of the current tile (ring positions persist across tiles)
     stamp(true);  // 0: start
@@ -575,7 +574,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
 
     for (int it = 0; tile < tend; ++it) {
       const bool t0 = it == 0;
-      const int nxt_tile = next_tile_zeroing(tile + tstep);
+      const int nxt_tile = next_tile(tile + tstep);
       const bool more = nxt_tile < tend;
       const int par = EDGE ? (it & 1) : 0;
       const uint32_t X = par ? ACC1 : ACC0, Y = par ? ACC0 : ACC1;

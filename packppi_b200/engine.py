@@ -78,7 +78,11 @@ class Graph:
         self.hE0 = None
         self._build()
 
+    _serial = 0
+
     def _build(self):
+        Graph._serial += 1
+        self.serial = Graph._serial  # identifies this set of masks (Workspace.clean_for)
         outs = (self.E_idx, self.nbr, self.D_neighbors, self.mask_attend, self.msum)
         if self.L >= CELL_LIST_MIN_L:  # cell list: O(L * neighbourhood); identical output
             if self._cells is None:
@@ -117,6 +121,7 @@ class Workspace:
         self.wsA, self.wsN, self.wsAcc = z(R, 128), z(R, 128), z(R, 128)
         self.wsP = z(R, 24)
         self.score = z(R, 4)
+        self.clean_for = None  # Graph.serial whose padding rows of hE / wsAcc are known to be zero
 
 
 class Engine:
@@ -184,6 +189,12 @@ class Engine:
         """node embedding + 3 IPMP layers on ws (rows S*G); leaves h_V in ws.hV."""
         G, K, S = graph.G, graph.K, ws.S
         W = self.wblob
+        if self.mode != "fp32" and ws.clean_for != graph.serial:
+            # the tensor-core kernels skip tiles that hold only padding residues: zero those rows once per graph
+            # (the CUDA-core kernels write the zeros themselves)
+            ws.hE.zero_()
+            ws.wsAcc.zero_()
+            ws.clean_for = graph.serial
         _lib.call("pp_node_embed", W, ni["rtype"], ni["bb"], chi, ni["chi_mask"], sc_sincos, t, t_stride, G, S, ws.hV)
         hE0 = graph.hE0 if hE0 is None else hE0
         for layer in range(3):

@@ -52,8 +52,9 @@ def test_sampling_tc(case, mode, cluster):
 
 
 def test_padding_tiles_are_skipped_and_zeroed():
-    """A batch padded to its longest complex: the tensor-core kernels skip the tiles that hold only padding residues
-    and must still leave zeros there (the buffers are poisoned first), identical to the CUDA-core kernels elsewhere."""
+    """A batch padded to its longest complex: the tensor-core kernels skip the tiles that hold only padding residues;
+    the engine zeroes those rows once per graph (the buffers are poisoned first), the rest must equal the CUDA-core
+    kernels."""
     from packppi_b200 import TDiffusionModule, weights, synthetic, _lib
     from packppi_b200.batch import collate
     dev = torch.device("cuda:0")
@@ -71,6 +72,7 @@ def test_padding_tiles_are_skipped_and_zeroed():
         ws = eng.workspace(graph.G, graph.K, 2)
         for buf in (ws.hE, ws.hV, ws.wsAcc):
             buf.fill_(float("nan"))
+        ws.clean_for = None
         ni = eng.node_inputs(batch)
         t = torch.full((2 * B * L,), 0.4, device=dev)
         eng.forward_layers(graph, ws, ni, chi.reshape(-1, 4).contiguous(), t, 1)
@@ -83,3 +85,31 @@ def test_padding_tiles_are_skipped_and_zeroed():
         assert hV[pad].abs().max().item() == 0.0 and hE.reshape(hV.shape[0], -1)[pad].abs().max().item() == 0.0, mode
     assert (outs["fp32"][0] - outs["f16x3"][0]).abs().max().item() < TOL["f16x3"]["act"]
     assert (outs["fp32"][1] - outs["f16x3"][1]).abs().max().item() < TOL["f16x3"]["act"]
+
+
+@pytest.mark.parametrize("mode", ["f16x3", "f16"])
+def test_repeated_evaluation_is_bit_identical(mode):
+    """All reductions of the tensor-core kernels have a fixed order, so repeating an evaluation must reproduce every
+    bit; a difference means a synchronisation bug (regression: a TMA copy once overtook shared-memory reads that were
+    still in flight, corrupting about one residue in 1000 tiles when the copy hit in L2)."""
+    from packppi_b200 import TDiffusionModule, weights, synthetic
+    from packppi_b200.batch import collate
+    dev = torch.device("cuda:0")
+    m = TDiffusionModule()
+    m.load_state_dict(weights.make_state_dict(0))
+    m.kernel_mode = mode
+    m = m.to(dev).eval()
+    for items, S in (([synthetic.make_complex((500, 500, 500), seed=3)], 2),
+                     ([synthetic.make_complex((20, 21), seed=1), synthetic.make_complex((190, 183), seed=2)], 4)):
+        b = collate(items).to(dev)
+        B, L = b.X.shape[:2]
+        x = ((torch.rand(S, B, L, 4, generator=torch.Generator().manual_seed(1)) * 2 - 1) * 3.14).to(dev)
+        eng, graph = m._graph(b)
+        t = torch.full((S * B * L,), 0.4, device=dev)
+        ref = None
+        for _ in range(30):
+            _, hV = eng.network(graph, b, x.reshape(-1, 4).contiguous(), t)
+            if ref is None:
+                ref = hV.clone()
+            else:
+                assert torch.equal(ref, hV)
