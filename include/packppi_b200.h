@@ -115,6 +115,14 @@ int pp_ipmp_node_post_tc(const float* weights, int64_t layer, const float* wstre
                          const float* residue_mask, int64_t G, int64_t K, int64_t S, const float* wsAcc, float* hV,
                          int64_t passes, int64_t cluster, pp_stream_t stream);
 
+/* Tensor-core version of pp_ipmp_node_pre (reference layers.py:72-77,91 and the h_V_i / h_V_j columns of W_in):
+ * tile = 128 residue rows, the three weight matrices resident in shared memory as fp16 (hi, lo) images.
+ * wstream = operand images of this layer and path (pp_tc_pre_stream_floats() floats, weights.pack_pre_stream). */
+int64_t pp_tc_pre_stream_floats(void);
+int pp_ipmp_node_pre_tc(const float* weights, int64_t layer, int64_t path, const float* wstream, const float* geo,
+                        int64_t G, int64_t S, const float* hV, float* wsA, float* wsN, float* wsP,
+                        pp_stream_t stream);
+
 /* Diagnostics: later pp_ipmp_edge_tc launches write clock64() stamps of the phase boundaries of their first tile
  * (CTA 0, one worker thread) into trace (device memory, >= 32 uint64); NULL switches it off. */
 int pp_set_tc_trace(uint64_t* trace);

@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 from . import _lib, tables
-from .weights import pack_tc_stream, pack_weights
+from .weights import pack_pre_stream, pack_tc_stream, pack_weights
 
 SIGMA_MIN, SIGMA_MAX = 0.01 * np.pi, np.pi  # schedule.py:148-149 defaults
 TOP_K = 32
@@ -153,6 +153,7 @@ class Engine:
         layout, total = _lib.layout()
         self.wblob = pack_weights(state_dict, layout, total).to(self.dev)
         self.wtc = pack_tc_stream(state_dict, _lib.load().pp_tc_stream_floats()).to(self.dev)
+        self.wpre = pack_pre_stream(state_dict, _lib.load().pp_tc_pre_stream_floats()).to(self.dev)
         self.tables = DeviceTables.get(self.dev)
         self._ws = {}
         self._sched = {}
@@ -208,7 +209,12 @@ class Engine:
                 continue
             tcp = (3 if self.mode == "f16x3" else 1, self.cluster)
             # the five kernels of a layer through their own entry points (instrumented fp32 mode, tensor-core modes)
-            _lib.call("pp_ipmp_node_pre", W, layer, 0, *common, *size, ws.hV, ws.wsA, ws.wsN, ws.wsP, rows=S * G)
+            node_tc = self.mode != "fp32" and self.node_epilogue == "tc"  # per-residue kernels on the tensor cores
+            pre = lambda path: (  # noqa: E731
+                _lib.call("pp_ipmp_node_pre_tc", W, layer, path, self.wpre[layer, path], graph.geo, G, S, ws.hV, ws.wsA,
+                          ws.wsN, ws.wsP, rows=S * G) if node_tc else
+                _lib.call("pp_ipmp_node_pre", W, layer, path, *common, *size, ws.hV, ws.wsA, ws.wsN, ws.wsP, rows=S * G))
+            pre(0)
             if self.mode == "fp32":
                 _lib.call("pp_ipmp_edge_node", W, layer, *common, *size, hE_in, shared, ws.wsA, ws.wsN, ws.wsP,
                           ws.wsAcc, rows=S * G)
@@ -223,7 +229,7 @@ class Engine:
                 _lib.call("pp_ipmp_node_post_tc", W, layer, self.wtc[layer, 2], graph.msum, graph.mask, G, K, S,
                           ws.wsAcc, ws.hV, 3, self.cluster, rows=S * G)
             if edge:
-                _lib.call("pp_ipmp_node_pre", W, layer, 1, *common, *size, ws.hV, ws.wsA, ws.wsN, ws.wsP, rows=S * G)
+                pre(1)
                 if self.mode == "fp32":
                     _lib.call("pp_ipmp_edge_edge", W, layer, *common, *size, hE_in, shared, ws.wsA, ws.wsN, ws.wsP,
                               ws.hE, rows=S * G)

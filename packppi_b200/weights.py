@@ -170,11 +170,11 @@ def _f16_scale(w):
 
 
 def _umma_image16(w):
-    """[128 rows, kc] K-major fp16 operand (int16 bit patterns) -> flat image in the no-swizzle core-matrix layout of
-    csrc/umma.cuh: element offset(row, k) = (k // 8) * 1024 + (row // 8) * 64 + (row % 8) * 8 + k % 8."""
+    """[rows, kc] K-major fp16 operand (int16 bit patterns) -> flat image in the no-swizzle core-matrix layout of
+    csrc/umma.cuh: element offset(row, k) = (k // 8) * rows * 8 + (row // 8) * 64 + (row % 8) * 8 + k % 8."""
     rows, kc = w.shape
-    assert rows == 128 and kc % 8 == 0
-    return w.reshape(16, 8, kc // 8, 8).permute(2, 0, 1, 3).contiguous().reshape(-1)
+    assert rows % 8 == 0 and kc % 8 == 0
+    return w.reshape(rows // 8, 8, kc // 8, 8).permute(2, 0, 1, 3).contiguous().reshape(-1)
 
 
 def pack_tc_stream(sd, stream_floats):
@@ -224,6 +224,38 @@ def pack_tc_stream(sd, stream_floats):
                     pieces += [_umma_image16(hi), _umma_image16(lo)]
             flat = torch.cat(pieces).view(torch.float32)
             assert flat.numel() <= stream_floats - 8
+            out[l, path, :flat.numel()] = flat
+            out[l, path, stream_floats - 8:] = inv
+    return out
+
+
+def pack_pre_stream(sd, stream_floats):
+    """Operand images for the tensor-core residue prologue (csrc/node_pre_tc.cu): [3 layers, 2 paths, stream_floats].
+
+    Per (layer, path: 0 = node message, 1 = edge message), each chunk of 32 k-columns as hi image then lo image:
+      W_p   points_fn weight [24 -> 32 rows, 128]                                     4 chunks of 32-row images
+      W_ag  W_in[:, h_V_i (0:128) | own geometry (384:416)]  [128, 160]               5 chunks
+      W_n   W_in[:, h_V_j (256:384)]                          [128, 128]               4 chunks
+    followed by 8 floats: 1 / scale of (W_p, W_ag, W_n)."""
+    check_state_dict(sd)
+    f = {k: v.detach().to("cpu", torch.float32) for k, v in sd.items()}
+    out = torch.zeros(N_LAYERS, 2, stream_floats, dtype=torch.float32)
+    for l in range(N_LAYERS):
+        p = f"mpnn.mpnn_layers.{l}."
+        for path, (pts, fn) in enumerate((("points_fn_node", "node_message_fn"), ("points_fn_edge", "edge_message_fn"))):
+            Win = f[p + fn + ".W_in.weight"]
+            Wp = torch.cat([f[p + pts + ".weight"], torch.zeros(8, H)], 0)
+            mats = [Wp, torch.cat([Win[:, 0:128], Win[:, 384:416]], 1), Win[:, 256:384]]
+            inv = torch.ones(8)
+            pieces = []
+            for i, M in enumerate(mats):
+                scale = _f16_scale(M)
+                inv[i] = 1.0 / scale
+                for k0 in range(0, M.shape[1], 32):
+                    hi, lo = _f16_split(M[:, k0:k0 + 32], scale)
+                    pieces += [_umma_image16(hi), _umma_image16(lo)]
+            flat = torch.cat(pieces).view(torch.float32)
+            assert flat.numel() == stream_floats - 8, (flat.numel(), stream_floats)
             out[l, path, :flat.numel()] = flat
             out[l, path, stream_floats - 8:] = inv
     return out

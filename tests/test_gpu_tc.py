@@ -113,3 +113,29 @@ def test_repeated_evaluation_is_bit_identical(mode):
                 ref = hV.clone()
             else:
                 assert torch.equal(ref, hV)
+
+
+@pytest.mark.parametrize("case", ["syn17", "synbatch", "t1124"])
+def test_node_pre_tc_matches_cuda_core_kernel(case):
+    """Residue prologue (IPMP points, A_i, N_j) on the tensor cores against the exact fp32 kernel, same inputs."""
+    from packppi_b200 import TDiffusionModule, weights, _lib
+    dev = torch.device("cuda:0")
+    g, b = load_golden(case)
+    bd = b.to(dev)
+    B, L = b.X.shape[:2]
+    m = _model(dev, "f16x3")
+    eng, graph = m._graph(bd)
+    G, K, S = graph.G, graph.K, 2
+    hV = torch.randn(S * G, 128, generator=torch.Generator().manual_seed(2)).to(dev)
+    W = eng.wblob
+    for layer in range(3):
+        for path in (0, 1):
+            ref = [torch.zeros(S * G, n, device=dev) for n in (128, 128, 24)]
+            out = [torch.full((S * G, n), float("nan"), device=dev) for n in (128, 128, 24)]
+            _lib.call("pp_ipmp_node_pre", W, layer, path, graph.geo, graph.nbr, graph.mask_attend, graph.mask, G, K, S,
+                      hV, *ref)
+            _lib.call("pp_ipmp_node_pre_tc", W, layer, path, eng.wpre[layer, path], graph.geo, G, S, hV, *out)
+            torch.cuda.synchronize()
+            for name, r, o in zip(("A", "N", "P"), ref, out):
+                scale = max(1.0, r.abs().max().item())
+                assert (r - o).abs().max().item() < 2e-5 * scale, (layer, path, name)
