@@ -75,18 +75,32 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
+
+    def wait_first_sample(self, timeout=10.0):
+        """nvidia-smi takes a moment to attach to the driver and that can stall kernel launches: the timed regions
+        start only after it is polling."""
+        t0 = time.monotonic()
+        while self.proc is not None and not self.rows and time.monotonic() - t0 < timeout:
+            time.sleep(0.05)
 
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+
+    def window(self, t0, t1):
+        """Summary of the samples taken between two time.monotonic() stamps."""
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for ts, r in list(self.rows):
+            if ts < t0 or ts > t1:
+                continue
             try:
                 sm.append(float(r[1]))
                 mx = float(r[2])
@@ -95,8 +109,8 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def build_sweep(n_complexes, seed_base, rank):
@@ -324,19 +338,30 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(args.warmup):
-        one_pass(micro_dev, False)
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local)  # one nvidia-smi poller for the whole run, started before the warm-up
     if rank == 0:
         clocks.start()
+    for _ in range(args.warmup):
+        one_pass(micro_dev, False)
+    if rank == 0:
+        clocks.wait_first_sample()
     _lib.LAUNCHES = 0
+    t_a = time.monotonic()
     ms = timed(micro_dev, False, args.steps)
+    t_b = time.monotonic()
     launches = _lib.LAUNCHES
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.window(t_a, t_b) if rank == 0 else None
     value = world * units * args.steps / (ms / 1e3)
 
-    one_pass(micro_pinned[:1], True)
+    one_pass(micro_pinned, True)  # warm-up of the host path: its allocations differ from the device-resident pass
+    t_a = time.monotonic()
+    if os.environ.get("PP_BENCH_DEBUG"):
+        for i in range(4):
+            print(f"[debug] e2e pass {i}: {timed(micro_pinned, True, 1):.1f} ms; device pass: "
+                  f"{timed(micro_dev, False, 1):.1f} ms", file=sys.stderr, flush=True)
     ms_e2e = timed(micro_pinned, True, max(1, min(args.steps, 2)))
+    clk_e2e = clocks.window(t_a, time.monotonic()) if rank == 0 else None
+    clocks.stop()
     e2e_steps = max(1, min(args.steps, 2))
     e2e_value = world * units * e2e_steps / (ms_e2e / 1e3)
     h2d = sum(b.nbytes() for b in micro_host)
@@ -396,7 +421,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(args), "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": "residue.steps/s", "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / e2e_steps},
+                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / e2e_steps, "clocks": clk_e2e},
                 "gpu_launches": launches, "residues_per_gpu": residues, "secondary": secondary}
         print(json.dumps(line))
     if world > 1:
