@@ -42,6 +42,9 @@ MICRO = 8
 EDGE_KERNEL_FLOP_PER_RES = 32 * 2 * (168 * 128 + 128 * 128 + 128 * 128 + 2 * 128 * 512)
 # algorithmic HBM bytes of the same launch per residue row: read h_E (K*128*4), write h_E (K*128*4), A, N gathers
 EDGE_KERNEL_BYTES_PER_RES = 2 * 32 * 128 * 4 + 2 * 128 * 4 + 24 * 4
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per valid residue row of the same kernel, from the
+# `ncu --set full` capture in profiles/r01_tc_f16x3_ncu_raw.csv: 966.6 MB for a launch over 29 616 valid rows
+NCU_EDGE_TRAFFIC_PER_RES = {"f16x3": 966.555e6 / 29616}
 
 
 def measured_peaks():
@@ -376,10 +379,13 @@ def main():
     _lib.PROFILE = None
     torch.cuda.synchronize()
     k_ms = [a.elapsed_time(b) for a, b, _ in ev]
-    k_rows = [r for _, _, r in ev]
+    # algorithmic work = the valid residues (padding rows of a ragged micro-batch are not work; the tensor-core
+    # kernels skip them).  Every micro-batch launches the kernel for 2 layers x 30 steps.
+    valid = sum(int(b.residue_mask.sum()) for b in micro_host) * N_SAMPLES
     peaks = measured_peaks()
     if k_ms:
-        tot_ms, tot_rows = sum(k_ms), sum(k_rows)
+        tot_ms, tot_rows = sum(k_ms), valid * 2 * N_ODE
+        assert len(k_ms) == len(micro_host) * 2 * N_ODE
         tflops = EDGE_KERNEL_FLOP_PER_RES * tot_rows / (tot_ms * 1e-3) / 1e12
         gbs = EDGE_KERNEL_BYTES_PER_RES * tot_rows / (tot_ms * 1e-3) / 1e9
         kname = {"fp32": "edge_edge_kernel (per-edge message MLP + FFN, fp32 FFMA on CUDA cores)",
@@ -389,7 +395,12 @@ def main():
         roof = {"kernel": kname, "bound": "tensor",
                 "achieved": tflops, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": tflops / peaks["tf_sust"],
                 "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
-                "traffic": None, "avg_launch_ms": tot_ms / len(k_ms), "launches": len(k_ms),
+                "traffic": (NCU_EDGE_TRAFFIC_PER_RES[mode] * tot_rows / len(k_ms)
+                            if mode in NCU_EDGE_TRAFFIC_PER_RES else None),
+                "traffic_note": "bytes per launch = ncu DRAM bytes per valid residue row (profiles/"
+                                "r01_tc_f16x3_ncu_raw.csv) x the average valid rows per launch of this run",
+                "algorithmic_bytes_per_launch": EDGE_KERNEL_BYTES_PER_RES * tot_rows / len(k_ms),
+                "avg_launch_ms": tot_ms / len(k_ms), "launches": len(k_ms),
                 "share_of_step": tot_ms / t_pass, "hbm_view": {"achieved_GBps": gbs, "peak_GBps": peaks["hbm"],
                                                               "frac": gbs / peaks["hbm"]},
                 "flop_per_residue_row": EDGE_KERNEL_FLOP_PER_RES, "bytes_per_residue_row": EDGE_KERNEL_BYTES_PER_RES}
