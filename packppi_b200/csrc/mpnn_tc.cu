@@ -4,8 +4,8 @@
 // split (only the 168-wide [h_E | pair geometry] part of the first Linear is per edge).  One CTA = one tile of 128
 // edges (4 residues x 32 neighbours) = the M dimension of a 128 x 128 UMMA; the whole GEMM chain of the tile stays on
 // chip:
-//   warps 0-7  row workers, two groups of 128 threads: thread (group, m) owns edge row m = TMEM lane m and two of the
-//              four 32-column chunks.  They build the first A operand, then act as the epilogue of every GEMM:
+//   workers    kGroups (4) groups of 128 threads = 16 warps: thread (group, m) owns edge row m = TMEM lane m and
+//              one of the four 32-column chunks (kGroups = 2: two chunks each, 8 warps).  They build the first A operand, then act as the epilogue of every GEMM:
 //              tcgen05.ld 32 columns -> bias / ReLU / LayerNorm -> next A operand, written into a shared-memory ring
 //              (or into TMEM for the FFN input); gathered rows are fetched before the wait on the accumulator
 //   warp 8     MMA issuer (one elected lane): tcgen05.mma kind::f16 (K = 16 per instruction), accumulators ping-pong
@@ -27,6 +27,8 @@
 // kind::tf32; 1 = hi only (11 bits, the precision of TF32; fast mode, looser tolerance).  Weight images are
 // pre-scaled by a power of two per matrix (weights.py: pack_tc_stream) so that their lo halves stay in the normal
 // fp16 range; the epilogues multiply the accumulator by the inverse scale (exact).
+#include <type_traits>
+
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 #include "common.cuh"
@@ -50,7 +52,14 @@ constexpr int kSA = PP_TC_SA;   // A ring: slots of 32 k-columns (fp16 hi + lo i
 constexpr int kSB = PP_TC_SB;   // B ring: slots of one weight chunk (<= 32 k-columns, hi + lo images, 16 KB)
 constexpr uint32_t kImgBytes = kRows * kKC * 2;  // one fp16 operand image (hi or lo) of a 32-column chunk: 8 KB
 constexpr uint32_t kSlotBytes = 2 * kImgBytes;   // hi + lo
-constexpr int kThreadsTC = 352;  // 8 worker warps (two groups of 128 rows), MMA warp, weight loader, tile loader
+#ifndef PP_TC_GROUPS
+#define PP_TC_GROUPS 2
+#endif
+constexpr int kGroups = PP_TC_GROUPS;      // worker threads per row: 2 (each owns two 32-column chunks) or 4 (one chunk)
+constexpr int kCPT = 4 / kGroups;          // chunks per thread: thread (grp, m) owns chunks grp, grp + kGroups, ...
+constexpr int kWorkers = kGroups * 128;
+constexpr int kWarpMMA = kWorkers / 32, kWarpWeights = kWarpMMA + 1, kWarpTiles = kWarpMMA + 2;
+constexpr int kThreadsTC = kWorkers + 96;  // worker warps, MMA warp, weight loader, tile loader
 constexpr uint32_t kLbo = kRows * 16, kSbo = 128;
 constexpr uint32_t kIdesc = idesc_f16(128, 128);
 constexpr int kPairKC = 16;                      // last G1 chunk: 8 pair distances padded to one K = 16 instruction
@@ -66,7 +75,7 @@ constexpr uint32_t kStageBytes = kRows * 128 * 4;  // one tile of h_E rows: 16 b
 // per-column parameters staged in shared memory (floats): b2, b3, LN2 gain/bias, FFN b_in (512), b_out, LN3 gain/bias
 constexpr int kP_B2 = 0, kP_B3 = 128, kP_LN2G = 256, kP_LN2B = 384, kP_BIN = 512, kP_BOUT = 1024, kP_LN3G = 1152,
               kP_LN3B = 1280, kParamFloats = 1408;
-constexpr int kRedFloats = 4 * 2 * 128;  // four row reductions x two groups
+constexpr int kRedFloats = 4 * kGroups * 128;  // four row reductions x groups
 constexpr size_t kSmemTC = kStageBytes + ((size_t)kSA + kSB) * kSlotBytes + kBarBytes + 16 +
                            (kParamFloats + kRedFloats) * 4;
 
@@ -216,10 +225,10 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
     for (int i = 0; i < kSB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], CLUSTER); }
     mbar_init(&acc_full[0], 1);
     mbar_init(&acc_full[1], 1);
-    mbar_init(wk_done, 256);
-    mbar_init(tile_done, 256);
+    mbar_init(wk_done, kWorkers);
+    mbar_init(tile_done, kWorkers);
     mbar_init(stage_full, 1);
-    mbar_init(stage_free, 256);
+    mbar_init(stage_free, kWorkers);
     mbar_fence_init();
   }
   {  // stage the per-column parameters
@@ -229,7 +238,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
       if ((EDGE || t == 0) && !(POST && t == 0))
         for (int i = tid; i < off[t + 1] - off[t]; i += kThreadsTC) prm[off[t] + i] = src[t][i];
   }
-  if (warp == 8) tmem_alloc<512>(tmem_slot);
+  if (warp == kWarpMMA) tmem_alloc<512>(tmem_slot);
   fence_before_sync();
   __syncthreads();
   if (CLUSTER > 1) cluster_sync_all();  // every CTA's barriers exist before any remote arrive / multicast
@@ -239,7 +248,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
   // in fp32 (residual), the other e as packed fp16 (hi: 64 columns, lo: 64 columns); the roles swap every tile
   const uint32_t ACC0 = tmem, ACC1 = tmem + 128, R0 = tmem + 256, R1 = tmem + 384;
 
-  if (warp == 9) {
+  if (warp == kWarpWeights) {
     // ------------------------------------------------------------------ weight loader
     if (lane == 0) {
       Ring rb_{0, 1};
@@ -265,7 +274,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
         }
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == kWarpTiles) {
     if (!POST && lane == 0) {
       // ---------------------------------------------------------------- h_E tile loader (TMA)
       // This thread owns the staging buffer.  Node message path: tile t+1 is fetched as soon as the workers have
@@ -313,40 +322,56 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
         }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == kWarpMMA) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp runs the control flow (waits included) so that it stays converged and the descriptor arithmetic
+    // lives in uniform registers; one elected lane issues the MMAs and commits of a chunk.
+    {
       Ring ra{0, 0}, rbq{0, 0};
       uint32_t wk_phase = 0, td_phase = 0;
       // ss: A from the shared-memory ring; otherwise a_tm = TMEM address of the packed hi half of the chunk (lo: + 64)
-      auto chunk = [&](bool ss, uint32_t acc, uint32_t a_tm, int kc, bool fresh) {
-        // pass 0: hi * hi, pass 1: hi * lo, pass 2: lo * hi
+      auto chunk_kc = [&](auto KC, bool ss, uint32_t acc, uint32_t a_tm, bool fresh) {
+        // pass 0: hi * hi, pass 1: hi * lo, pass 2: lo * hi.  Descriptors: low word of the slot start + a constant
+        constexpr int kc = decltype(KC)::value;
         if (ss) mbar_wait(&a_full[ra.idx], ra.phase);
-        const uint32_t as = smem_u32(Aring + ra.idx * kSlotBytes);
+        const uint32_t a_lo = desc_lo(smem_u32(Aring + ra.idx * kSlotBytes), kLbo);
         mbar_wait(&b_full[rbq.idx], rbq.phase);
         fence_after_sync();
-        const uint32_t bs = smem_u32(Bring + rbq.idx * kSlotBytes);
-        const uint32_t blo = (uint32_t)kRows * kc * 2;
+        const uint32_t b_lo = desc_lo(smem_u32(Bring + rbq.idx * kSlotBytes), kLbo);
+        constexpr uint32_t kHi = desc_hi(kSbo);
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int p = 0; p < PASSES; ++p) {
-          const uint32_t ao = (p == 2) ? kImgBytes : 0, bo = (p == 1) ? blo : 0;
-          for (int kk = 0; kk < kc; kk += 16) {
-            const uint64_t bd = smem_desc(bs + bo + (kk / 8) * kLbo, kLbo, kSbo);
-            const uint32_t accum = (fresh && p == 0 && kk == 0) ? 0u : 1u;
-            if (ss) mma_f16_ss(acc, smem_desc(as + ao + (kk / 8) * kLbo, kLbo, kSbo), bd, kIdesc, accum);
-            else mma_f16_ts(acc, a_tm + ((p == 2) ? 64 : 0) + kk / 2, bd, kIdesc, accum);
+          for (int p = 0; p < PASSES; ++p) {
+#pragma unroll
+            for (int kk = 0; kk < kc; kk += 16) {
+              const uint32_t ad = (((p == 2) ? kImgBytes : 0u) + (kk / 8) * kLbo) >> 4;
+              const uint32_t bd = (((p == 1) ? (uint32_t)kRows * kc * 2 : 0u) + (kk / 8) * kLbo) >> 4;
+              const uint32_t accum = (fresh && p == 0 && kk == 0) ? 0u : 1u;
+              if (ss) mma_f16_ss2(acc, a_lo + ad, b_lo + bd, kHi, kIdesc, accum);
+              else mma_f16_ts2(acc, a_tm + ((p == 2) ? 64 : 0) + kk / 2, b_lo + bd, kHi, kIdesc, accum);
+            }
           }
+          if (CLUSTER == 1) mma_commit(&b_empty[rbq.idx]); else mma_commit_mc(&b_empty[rbq.idx], kMask);
+          if (ss) mma_commit(&a_empty[ra.idx]);
         }
-        if (CLUSTER == 1) mma_commit(&b_empty[rbq.idx]); else mma_commit_mc(&b_empty[rbq.idx], kMask);
+        __syncwarp();
         rbq.next(kSB);
-        if (ss) { mma_commit(&a_empty[ra.idx]); ra.next(kSA); }
+        if (ss) ra.next(kSA);
+      };
+      auto commit_acc = [&](int bar) {
+        if (elect_one_sync()) mma_commit(&acc_full[bar]);
+        __syncwarp();
+      };
+      auto chunk = [&](bool ss, uint32_t acc, uint32_t a_tm, int kc, bool fresh) {
+        if (kc == kKC) chunk_kc(std::integral_constant<int, kKC>{}, ss, acc, a_tm, fresh);
+        else chunk_kc(std::integral_constant<int, kPairKC>{}, ss, acc, a_tm, fresh);
       };
       auto wait_workers = [&]() { mbar_wait(wk_done, wk_phase); wk_phase ^= 1; fence_after_sync(); };
       // first GEMM of a tile: G1 = [h_E | pair] (176 wide) of the message MLP, or W3 of the node epilogue
       auto head = [&](uint32_t acc, int bar) {
         if (!POST) { for (int c = 0; c < 6; ++c) chunk(true, acc, 0, c == 5 ? kPairKC : kKC, c == 0); }
         else       { for (int c = 0; c < 4; ++c) chunk(true, acc, 0, kKC, c == 0); }
-        mma_commit(&acc_full[bar]);
+        commit_acc(bar);
       };
       // Tiles are software-pipelined: the head GEMM of tile it+1 is issued before the workers run the last epilogue of
       // tile it.  In the EDGE modes the roles of the two accumulators (X: head, G3, FFN-out; Y: G2, FFN-in) and of
@@ -366,7 +391,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
         }
         if (!POST) {
           for (int c = 0; c < 4; ++c) chunk(true, Y, 0, kKC, c == 0);  // G2
-          mma_commit(&acc_full[yb]);
+          commit_acc(yb);
         }
         if (!EDGE) {
           // G2's operand chunks exist only once every worker has drained ACC0, so the next G1 may follow directly
@@ -375,22 +400,22 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
         }
         if (!POST) {
           for (int c = 0; c < 4; ++c) chunk(true, X, 0, kKC, c == 0);  // G3
-          mma_commit(&acc_full[xb]);
+          commit_acc(xb);
         }
         // FFN, software-pipelined by one slice: while the workers turn slice j into the A operand of FFN-out j,
         // the tensor pipe runs FFN-out j-1 and FFN-in j+1
         wait_workers();  // e is in TMEM, X / Y are drained
         for (int c = 0; c < 4; ++c) chunk(false, Y, PK + c * (kKC / 2), kKC, c == 0);  // FFN-in slice 0: A = e (TMEM)
-        mma_commit(&acc_full[yb]);
+        commit_acc(yb);
         for (int j = 0; j < 4; ++j) {
           if (j + 1 < 4) {
             wait_workers();  // slice j has been read out of Y
             for (int c = 0; c < 4; ++c) chunk(false, Y, PK + c * (kKC / 2), kKC, c == 0);  // FFN-in slice j+1
-            mma_commit(&acc_full[yb]);
+            commit_acc(yb);
           }
           for (int c = 0; c < 4; ++c) chunk(true, X, 0, kKC, j == 0 && c == 0);  // FFN-out slice j accumulates
         }
-        mma_commit(&acc_full[xb]);
+        commit_acc(xb);
         if (more) {
           wait_workers();  // slice 3 has been read out of Y, which becomes the X of the next tile
           head(Y, yb);
@@ -399,8 +424,8 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
     }
   } else {
     // ------------------------------------------------------------------ row workers
-    // Two groups of 128 threads; thread (grp, m) owns edge row m (= TMEM lane m) and the column chunks {grp, grp + 2}
-    // of every 128-wide activation, so consecutive A chunks are produced by alternating groups.
+    // kGroups groups of 128 threads; thread (grp, m) owns edge row m (= TMEM lane m) and the 32-column chunks
+    // grp, grp + kGroups, ... of every 128-wide activation, so the A chunks of an operand are produced side by side.
     const int grp = tid >> 7, m = tid & 127, rl = m >> 5, k = lane;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t accph[2] = {0, 0};
@@ -440,10 +465,13 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
       c.hrow = a.hE_in + ((size_t)(a.he_shared ? c.g : c.rr) * K + (c.in_range ? k : 0)) * 128;
       return c;
     };
-    auto row_total = [&](float partial, int which) -> float {  // sum over the two threads that share a row
-      red[(which * 2 + grp) * 128 + m] = partial;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      return red[(which * 2) * 128 + m] + red[(which * 2 + 1) * 128 + m];
+    auto row_total = [&](float partial, int which) -> float {  // sum over the threads that share a row
+      red[(which * kGroups + grp) * 128 + m] = partial;
+      asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory");
+      float tot = red[(which * kGroups) * 128 + m];
+#pragma unroll
+      for (int g2 = 1; g2 < kGroups; ++g2) tot += red[(which * kGroups + g2) * 128 + m];
+      return tot;
     };
     uint32_t sf_phase = 0;
     // this thread's row in the staging buffer; 16-byte unit u of chunk c sits at (c << 14) + ((u ^ (k & 7)) << 4)
@@ -479,32 +507,32 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
     //      path, first tile); otherwise the edge update's result rows of the previous tile do that.
     auto first_operand = [&](const RowCtx& c, int qb, uint32_t stash, bool release) {
       float v[32];
-      float4 h[2][8];
+      float4 h[kCPT][8];
       if (POST) {
 #pragma unroll
-        for (int t = 0; t < 2; ++t)
+        for (int t = 0; t < kCPT; ++t)
 #pragma unroll
           for (int u = 0; u < 8; ++u)
-            h[t][u] = c.in_range ? *reinterpret_cast<const float4*>(c.hrow + (grp + 2 * t) * 32 + u * 4)
+            h[t][u] = c.in_range ? *reinterpret_cast<const float4*>(c.hrow + (grp + kGroups * t) * 32 + u * 4)
                                  : make_float4(0.f, 0.f, 0.f, 0.f);
       } else {
         mbar_wait(stage_full, sf_phase); sf_phase ^= 1;
 #pragma unroll
-        for (int t = 0; t < 2; ++t)
+        for (int t = 0; t < kCPT; ++t)
 #pragma unroll
           for (int u = 0; u < 8; ++u)
-            h[t][u] = c.in_range ? *reinterpret_cast<const float4*>(srow + ((grp + 2 * t) << 14) + ((u ^ swz) << 4))
+            h[t][u] = c.in_range ? *reinterpret_cast<const float4*>(srow + ((grp + kGroups * t) << 14) + ((u ^ swz) << 4))
                                  : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       if (POST) {
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
+        for (int t = 0; t < kCPT; ++t) {
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             v[u * 4] = h[t][u].x * a.in_scale; v[u * 4 + 1] = h[t][u].y * a.in_scale;
             v[u * 4 + 2] = h[t][u].z * a.in_scale; v[u * 4 + 3] = h[t][u].w * a.in_scale;
           }
-          publish(qb + grp + 2 * t, v, kKC);
+          publish(qb + grp + kGroups * t, v, kKC);
         }
         return;
       }
@@ -512,10 +540,12 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
       const float4* pi4 = reinterpret_cast<const float4*>(a.pglob + (size_t)c.rr * 24);
       const float4* pj4 = reinterpret_cast<const float4*>(a.pglob + (size_t)c.jrow * 24);
       float fr[12], pi[24], pj[24];
+      if (grp < 2) {
 #pragma unroll
-      for (int u = 0; u < 6; ++u) {
-        float4 x = pj4[u];
-        pj[u * 4] = x.x; pj[u * 4 + 1] = x.y; pj[u * 4 + 2] = x.z; pj[u * 4 + 3] = x.w;
+        for (int u = 0; u < 6; ++u) {
+          float4 x = pj4[u];
+          pj[u * 4] = x.x; pj[u * 4 + 1] = x.y; pj[u * 4 + 2] = x.z; pj[u * 4 + 3] = x.w;
+        }
       }
       if (grp == 0) {
 #pragma unroll
@@ -523,7 +553,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
           float4 x = fr4[u];
           fr[u * 4] = x.x; fr[u * 4 + 1] = x.y; fr[u * 4 + 2] = x.z; fr[u * 4 + 3] = x.w;
         }
-      } else {
+      } else if (grp == 1) {
 #pragma unroll
         for (int u = 0; u < 6; ++u) {
           float4 x = pi4[u];
@@ -531,19 +561,20 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
         }
       }
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
+      for (int t = 0; t < kCPT; ++t) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           v[u * 4] = h[t][u].x; v[u * 4 + 1] = h[t][u].y; v[u * 4 + 2] = h[t][u].z; v[u * 4 + 3] = h[t][u].w;
         }
-        if (MODE == 1) store_tmem(stash + (grp + 2 * t) * 32, v);
-        publish(qb + grp + 2 * t, v, kKC);
+        if (MODE == 1) store_tmem(stash + (grp + kGroups * t) * 32, v);
+        publish(qb + grp + kGroups * t, v, kKC);
       }
       // Hand the buffer back only now: the rows have provably left shared memory (their values were consumed by the
       // stores above).  Arriving right after issuing the loads let the next TMA copy overtake reads still in flight
       // (measured: one corrupted residue in ~1000 tiles when the copy hits in L2).
       if (release) mbar_arrive(stage_free);
       if (MODE == 1) tmem_st_wait();
+      if (grp >= 2) return;  // the pair geometry is built by groups 0 (frames) and 1 (distances)
       float geo[32];
 #pragma unroll
       for (int i = 8; i < kPairKC; ++i) geo[i] = 0.f;  // zero padding of the distance chunk (group 1)
@@ -591,21 +622,21 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
       if (!POST) {
         const float* Ai = a.A + (size_t)rr * 128;
         const float* Nj = a.Nn + (size_t)cx.jrow * 128;
-        float4 an[2][8];
+        float4 an[kCPT][8];
 #pragma unroll
-        for (int t = 0; t < 2; ++t)
+        for (int t = 0; t < kCPT; ++t)
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            float4 x = *reinterpret_cast<const float4*>(Ai + (grp + 2 * t) * 32 + u * 4);
-            float4 y = *reinterpret_cast<const float4*>(Nj + (grp + 2 * t) * 32 + u * 4);
+            float4 x = *reinterpret_cast<const float4*>(Ai + (grp + kGroups * t) * 32 + u * 4);
+            float4 y = *reinterpret_cast<const float4*>(Nj + (grp + kGroups * t) * 32 + u * 4);
             an[t][u] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
           }
         mbar_wait(&acc_full[xb], accph[xb]); accph[xb] ^= 1;
         fence_after_sync();
         stamp(t0);  // 2: G1 complete
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          load_acc(X, grp + 2 * t, v);
+        for (int t = 0; t < kCPT; ++t) {
+          load_acc(X, grp + kGroups * t, v);
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             v[u * 4 + 0] = fmaxf(fmaf(v[u * 4 + 0], sG1, an[t][u].x), 0.f);
@@ -613,7 +644,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
             v[u * 4 + 2] = fmaxf(fmaf(v[u * 4 + 2], sG1, an[t][u].z), 0.f);
             v[u * 4 + 3] = fmaxf(fmaf(v[u * 4 + 3], sG1, an[t][u].w), 0.f);
           }
-          publish(qbase + 6 + grp + 2 * t, v, kKC);
+          publish(qbase + 6 + grp + kGroups * t, v, kKC);
         }
         stamp(t0);  // 3: x1 published
       }
@@ -626,8 +657,8 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
         stamp(t0);  // 4: G2 complete
         // masked sum over the 32 edges of the residue (= the 32 lanes of this warp), layers.py:125-127
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int c = grp + 2 * t;
+        for (int t = 0; t < kCPT; ++t) {
+          const int c = grp + kGroups * t;
           load_acc(ACC1, c, v);
           const float* b = prm + kP_B2 + c * 32;
 #pragma unroll
@@ -653,8 +684,8 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
           fence_after_sync();
           stamp(t0);  // 4: G2 complete
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const int c = grp + 2 * t;
+          for (int t = 0; t < kCPT; ++t) {
+            const int c = grp + kGroups * t;
             load_acc(Y, c, v);
             const float* b = prm + kP_B2 + c * 32;
 #pragma unroll
@@ -665,24 +696,24 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
         }
         // ---- epilogue of G3: e = LN2(h_E + mask * (acc + b3))   (layers.py:139-142); e -> TMEM (fp32 and packed fp16)
         {
-          float4 h[2][8];
+          float4 h[kCPT][8];
           if (POST) {  // residual = h_V of the residue; b3 enters scaled by the mean attention mask (layers.py:125-128)
             const float* hv = a.hres + (size_t)rr * 128;
 #pragma unroll
-            for (int t = 0; t < 2; ++t)
+            for (int t = 0; t < kCPT; ++t)
 #pragma unroll
-              for (int u = 0; u < 8; ++u) h[t][u] = *reinterpret_cast<const float4*>(hv + (grp + 2 * t) * 32 + u * 4);
+              for (int u = 0; u < 8; ++u) h[t][u] = *reinterpret_cast<const float4*>(hv + (grp + kGroups * t) * 32 + u * 4);
           }
           const float bscale = POST ? a.msum[cx.g] : 1.f;
           const bool gate = POST ? true : on;
           mbar_wait(&acc_full[xb], accph[xb]); accph[xb] ^= 1;
           fence_after_sync();
           stamp(t0);  // 6: G3 complete
-          float x[2][32];
+          float x[kCPT][32];
           float sum = 0.f;
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const int c = grp + 2 * t;
+          for (int t = 0; t < kCPT; ++t) {
+            const int c = grp + kGroups * t;
             if (POST) {
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
@@ -702,13 +733,13 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
           const float mean = row_total(sum, 0) * (1.f / 128.f);
           float var = 0.f;
 #pragma unroll
-          for (int t = 0; t < 2; ++t)
+          for (int t = 0; t < kCPT; ++t)
 #pragma unroll
             for (int i = 0; i < 32; ++i) { float d = x[t][i] - mean; var += d * d; }
           const float rstd = rsqrtf(row_total(var, 1) * (1.f / 128.f) + 1e-5f);
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const int c = grp + 2 * t;
+          for (int t = 0; t < kCPT; ++t) {
+            const int c = grp + kGroups * t;
             const float* gm = prm + kP_LN2G + c * 32;
             const float* bt = prm + kP_LN2B + c * 32;
             uint32_t eh[16], el[16];
@@ -732,14 +763,14 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
           stamp(t0);  // 8 + 2j: FFN-in slice j complete
           float v2[32];
           load_acc(Y, grp, v);
-          load_acc(Y, grp + 2, v2);
+          if (kCPT == 2) load_acc(Y, grp + kGroups, v2);
           // Y is drained for this thread: the next FFN-in slice / the next tile's head may overwrite it.  Signalled
           // before the chunks are published, which can block on a ring slot that only FFN-out j-1 frees.
           fence_before_sync();
           mbar_arrive(wk_done);
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const int c = grp + 2 * t;
+          for (int t = 0; t < kCPT; ++t) {
+            const int c = grp + kGroups * t;
             const float* b = prm + kP_BIN + j * 128 + c * 32;
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(fmaf(t ? v2[i] : v[i], sFI, b[i]), 0.f);
@@ -755,11 +786,11 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
         mbar_wait(&acc_full[xb], accph[xb]); accph[xb] ^= 1;
         fence_after_sync();
         stamp(t0);  // 17: FFN-out complete
-        float y[2][32];
+        float y[kCPT][32];
         float sum = 0.f;
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int c = grp + 2 * t;
+        for (int t = 0; t < kCPT; ++t) {
+          const int c = grp + kGroups * t;
           load_acc(RE, c, y[t]);
           load_acc(X, c, v);
           const float* b = prm + kP_BOUT + c * 32;
@@ -769,7 +800,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
         const float mean3 = row_total(sum, 2) * (1.f / 128.f);
         float var = 0.f;
 #pragma unroll
-        for (int t = 0; t < 2; ++t)
+        for (int t = 0; t < kCPT; ++t)
 #pragma unroll
           for (int i = 0; i < 32; ++i) { float d = y[t][i] - mean3; var += d * d; }
         const float rstd3 = rsqrtf(row_total(var, 3) * (1.f / 128.f) + 1e-5f);
@@ -778,8 +809,8 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
         float* orow = a.out + (size_t)rr * 128;
         if (in_range || !POST) {
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const int c = grp + 2 * t;
+          for (int t = 0; t < kCPT; ++t) {
+            const int c = grp + kGroups * t;
             const float* gm = prm + kP_LN3G + c * 32;
             const float* bt = prm + kP_LN3B + c * 32;
 #pragma unroll
@@ -815,7 +846,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
   fence_before_sync();
   __syncthreads();
   if (CLUSTER > 1) cluster_sync_all();
-  if (warp == 8) tmem_dealloc<512>(tmem);
+  if (warp == kWarpMMA) tmem_dealloc<512>(tmem);
 }
 
 // Tensor map of a [rows][K][128] fp32 tensor with boxes {32 floats, min(K, 32) rows, 1}: one residue's rows of one

@@ -95,24 +95,30 @@ __global__ void __launch_bounds__(kThreads, 1) node_pre_tc_kernel(const Args a) 
   const uint32_t ACC_A = tmem, ACC_N = tmem + 128, ACC_P = tmem + 256;
 
   if (warp == 8) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- weights in, then MMA issue
-      mbar_arrive_expect_tx(w_full, kWBytes);
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wstream);
-      for (uint32_t off = 0; off < kWBytes; off += 16384) bulk_g2s(smem + off, src + off, 16384, w_full);
+    {
+      // ---------------------------------------------------------------- weights in, then MMA issue (the warp stays
+      // converged: all lanes run the control flow, one elected lane issues)
+      if (lane == 0) {
+        mbar_arrive_expect_tx(w_full, kWBytes);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wstream);
+        for (uint32_t off = 0; off < kWBytes; off += 16384) bulk_g2s(smem + off, src + off, 16384, w_full);
+      }
+      __syncwarp();
       mbar_wait(w_full, 0);
       constexpr uint32_t kIdescP = idesc_f16(128, 32), kIdescW = idesc_f16(128, 128);
       int q = 0;
       uint32_t td_phase = 0;
       // one ring slot against one resident weight chunk: hi*hi, hi*lo, lo*hi
       auto gemm = [&](uint32_t acc, uint32_t as, uint32_t bs, uint32_t b_lo, uint32_t b_lbo, uint32_t idesc, bool fresh) {
+        const uint32_t a0 = desc_lo(as, kLbo), b0 = desc_lo(bs, b_lbo);
+        constexpr uint32_t kHi = desc_hi(kSbo);
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
           const uint32_t ao = (p == 2) ? kImgBytes : 0, bo = (p == 1) ? b_lo : 0;
 #pragma unroll
           for (int kk = 0; kk < kKC; kk += 16)
-            mma_f16_ss(acc, smem_desc(as + ao + (kk / 8) * kLbo, kLbo, kSbo),
-                       smem_desc(bs + bo + (kk / 8) * b_lbo, b_lbo, kSbo), idesc, (fresh && p == 0 && kk == 0) ? 0u : 1u);
+            mma_f16_ss2(acc, a0 + ((ao + (kk / 8) * kLbo) >> 4), b0 + ((bo + (kk / 8) * b_lbo) >> 4), kHi, idesc,
+                        (fresh && p == 0 && kk == 0) ? 0u : 1u);
         }
       };
       for (int tile = blockIdx.x, it = 0; tile < ntiles; tile += gridDim.x, ++it) {
@@ -122,15 +128,18 @@ __global__ void __launch_bounds__(kThreads, 1) node_pre_tc_kernel(const Args a) 
           mbar_wait(&a_full[slot], (q / kSA) & 1);
           fence_after_sync();
           const uint32_t as = smem_u32(Aring + slot * kSlotBytes);
-          if (c < 4) {
-            gemm(ACC_P, as, smem_u32(Wp + c * 2 * kPImgBytes), kPImgBytes, kPLbo, kIdescP, c == 0);
-            gemm(ACC_N, as, smem_u32(Wn + c * kSlotBytes), kImgBytes, kLbo, kIdescW, c == 0);
+          if (elect_one_sync()) {
+            if (c < 4) {
+              gemm(ACC_P, as, smem_u32(Wp + c * 2 * kPImgBytes), kPImgBytes, kPLbo, kIdescP, c == 0);
+              gemm(ACC_N, as, smem_u32(Wn + c * kSlotBytes), kImgBytes, kLbo, kIdescW, c == 0);
+            }
+            gemm(ACC_A, as, smem_u32(Wag + c * kSlotBytes), kImgBytes, kLbo, kIdescW, c == 0);
+            mma_commit(&a_empty[slot]);
+            if (c == 3) mma_commit(p_full);
+            if (c == 4) mma_commit(an_full);
           }
-          gemm(ACC_A, as, smem_u32(Wag + c * kSlotBytes), kImgBytes, kLbo, kIdescW, c == 0);
-          mma_commit(&a_empty[slot]);
-          if (c == 3) mma_commit(p_full);
+          __syncwarp();
         }
-        mma_commit(an_full);
       }
     }
   } else {
