@@ -259,3 +259,39 @@ def test_gather_owned_rows_over_two_gloo_ranks():
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res)
+
+
+def test_tensor_core_operand_images_decode_back_to_the_weights():
+    """pack_tc_stream / pack_pre_stream: fp16 (hi, lo) image pairs in UMMA core-matrix order, scaled by a power of
+    two; decoding an image with the documented offset formula must give the weight back to ~2^-22."""
+    import torch
+    from packppi_b200 import weights
+    sd = weights.make_state_dict(0)
+
+    def decode(words, off_halves, rows, kc):
+        """-> (hi + lo) as [rows, kc] float64 from the image pair that starts at `off_halves` (int16 units)."""
+        raw = words.view(torch.int16)
+        n = rows * kc
+        hi = raw[off_halves:off_halves + n].view(torch.float16).double()
+        lo = raw[off_halves + n:off_halves + 2 * n].view(torch.float16).double()
+        r = torch.arange(rows).view(-1, 1)
+        k = torch.arange(kc).view(1, -1)
+        idx = (k // 8) * rows * 8 + (r // 8) * 64 + (r % 8) * 8 + k % 8
+        return (hi + lo)[idx]
+
+    n_tc = 2 * 128 * (176 + 128 + 128 + 4 * 256) * 2 // 4 + 8
+    w = weights.pack_tc_stream(sd, n_tc)
+    assert w.shape == (3, 3, n_tc)
+    M = sd["mpnn.mpnn_layers.1.edge_message_fn.W_inter.0.weight"].double()        # G2 of layer 1, edge path
+    inv = float(w[1, 1, n_tc - 8 + 1])
+    got = decode(w[1, 1], 2 * 128 * 176 + 2 * 128 * 32 * 2, 128, 32) * inv         # third chunk: k = 64..95
+    assert (got - M[:, 64:96]).abs().max().item() < 2 ** -21 * M.abs().max().item()
+    assert inv == 2.0 ** round(np.log2(inv))
+
+    n_pre = (4 * 2 * 32 * 32 * 2 + 9 * 2 * 128 * 32 * 2) // 4 + 8
+    p = weights.pack_pre_stream(sd, n_pre)
+    assert p.shape == (3, 2, n_pre)
+    Wp = sd["mpnn.mpnn_layers.2.points_fn_edge.weight"].double()                   # [24, 128]
+    got = decode(p[2, 1], 2 * 32 * 32, 32, 32) * float(p[2, 1, n_pre - 8])         # second chunk: k = 32..63
+    assert (got[:24] - Wp[:, 32:64]).abs().max().item() < 2 ** -21 * Wp.abs().max().item()
+    assert got[24:].abs().max().item() == 0.0
