@@ -7,6 +7,9 @@
 //   rows  ty*4 + {0..3} and 64 + ty*4 + {0..3}      cols  tx*4 + {0..3} and 64 + tx*4 + {0..3}
 // so that every shared-memory read is a conflict-free 128-bit access.
 #pragma once
+#ifndef PP_USE_FFMA2
+#define PP_USE_FFMA2 1
+#endif
 #include "common.cuh"
 
 namespace pp {
@@ -66,6 +69,15 @@ __device__ __forceinline__ void gemm_tile(float (&acc)[8][8], const float* As, i
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float av = (q == 0) ? a[i].x : (q == 1) ? a[i].y : (q == 2) ? a[i].z : a[i].w;
+#if PP_USE_FFMA2
+          // packed fp32 FMA (sm_100): two IEEE fmas per instruction, same results, half the issue slots
+          const float2 a2 = make_float2(av, av);
+          float2 r;
+          r = __ffma2_rn(a2, make_float2(b0.x, b0.y), make_float2(acc[i][0], acc[i][1])); acc[i][0] = r.x; acc[i][1] = r.y;
+          r = __ffma2_rn(a2, make_float2(b0.z, b0.w), make_float2(acc[i][2], acc[i][3])); acc[i][2] = r.x; acc[i][3] = r.y;
+          r = __ffma2_rn(a2, make_float2(b1.x, b1.y), make_float2(acc[i][4], acc[i][5])); acc[i][4] = r.x; acc[i][5] = r.y;
+          r = __ffma2_rn(a2, make_float2(b1.z, b1.w), make_float2(acc[i][6], acc[i][7])); acc[i][6] = r.x; acc[i][7] = r.y;
+#else
           acc[i][0] = fmaf(av, b0.x, acc[i][0]);
           acc[i][1] = fmaf(av, b0.y, acc[i][1]);
           acc[i][2] = fmaf(av, b0.z, acc[i][2]);
@@ -74,6 +86,7 @@ __device__ __forceinline__ void gemm_tile(float (&acc)[8][8], const float* As, i
           acc[i][5] = fmaf(av, b1.y, acc[i][5]);
           acc[i][6] = fmaf(av, b1.z, acc[i][6]);
           acc[i][7] = fmaf(av, b1.w, acc[i][7]);
+#endif
         }
       }
     }

@@ -1,0 +1,47 @@
+"""Accuracy of the execution modes against the CPU oracle on fresh random inputs (run on the GPU box):
+max chi difference after 2 and after 30 reverse-ODE steps, several seeds."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+
+
+def main():
+    from oracle import msc_oracle as mo
+    from oracle import prox_oracle as po
+    from packppi_b200 import TDiffusionModule, synthetic, weights
+    dev = torch.device("cuda:0")
+    sd = weights.make_state_dict(0)
+    configs = (("fp32", "ffma"), ("f16x3", "ffma"), ("f16x3", "tc"))
+    models = {}
+    for mode, ne in configs:
+        m = TDiffusionModule()
+        m.load_state_dict(sd)
+        m.kernel_mode, m.kernel_node_epilogue = mode, ne
+        models[(mode, ne)] = m.to(dev).eval()
+    worst = {c: [0.0, 0.0] for c in configs}
+    for seed in range(int(sys.argv[1]) if len(sys.argv) > 1 else 6):
+        b = synthetic.make_complex((40 + 3 * seed, 24 + seed), seed=seed, place_side_chains=po.atom14_coords)
+        L = b.X.shape[1]
+        g = torch.Generator().manual_seed(100 + seed)
+        x0 = ((torch.rand(1, L, 4, generator=g) * 2 - 1) * 3.14159) * b.SC_D_mask
+        refs = {n: mo.sampling(sd, b, x0, n_steps=n) for n in (2, 30)}
+        bd = b.to(dev)
+        line = [f"seed {seed} L {L:3d}"]
+        for c in configs:
+            eng, graph = models[c]._graph(bd)
+            for i, n in enumerate((2, 30)):
+                chi = eng.sample(graph, bd, x0.reshape(-1, 4).to(dev), n_steps=n).cpu().reshape(1, L, 4)
+                d = (chi - refs[n]).abs()
+                d = torch.minimum(d, 2 * 3.141592653589793 - d).max().item()
+                worst[c][i] = max(worst[c][i], d)
+                line.append(f"{c[0]}/{c[1]} n={n}: {d:.1e}")
+        print("  ".join(line), flush=True)
+    for c in configs:
+        print(f"worst {c[0]}/{c[1]}: 2 steps {worst[c][0]:.2e}, 30 steps {worst[c][1]:.2e}")
+
+
+if __name__ == "__main__":
+    main()
