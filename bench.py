@@ -178,7 +178,7 @@ def run_reference(args):
 
 def workload_config(args):
     return {"kernel_mode": os.environ.get("PACKPPI_B200_MODE", "f16x3"),
-            "kernel_node_epilogue": os.environ.get("PACKPPI_B200_NODE_EPILOGUE") or "mode default (f16x3: ffma)",
+            "kernel_node_epilogue": os.environ.get("PACKPPI_B200_NODE_EPILOGUE") or "tc32",
             "kernel_cluster": int(os.environ.get("PACKPPI_B200_CLUSTER", "1")),
             "workload": f"sweep of {args.complexes} synthetic 2-chain complexes, L~U{{200..800}} (seed 64) x "
                         f"{N_SAMPLES} diffusion samples x {N_ODE} reverse-ODE steps, micro-batches of {MICRO} complexes; "

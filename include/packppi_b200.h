@@ -115,6 +115,13 @@ int pp_ipmp_node_post_tc(const float* weights, int64_t layer, const float* wstre
                          const float* residue_mask, int64_t G, int64_t K, int64_t S, const float* wsAcc, float* hV,
                          int64_t passes, int64_t cluster, pp_stream_t stream);
 
+/* pp_ipmp_node_post on the tensor cores with fp32-grade ("promoted") accumulation: every K = 16 step of a GEMM goes
+ * into a fresh TMEM accumulator and the row threads sum the steps in fp32 registers, because the tensor core's own
+ * fp32 accumulation truncates (csrc/node_post_tc.cu).  Same arguments as pp_ipmp_node_post_tc. */
+int pp_ipmp_node_post_tc32(const float* weights, int64_t layer, const float* wstream, const float* msum,
+                           const float* residue_mask, int64_t G, int64_t K, int64_t S, const float* wsAcc, float* hV,
+                           pp_stream_t stream);
+
 /* Tensor-core version of pp_ipmp_node_pre (reference layers.py:72-77,91 and the h_V_i / h_V_j columns of W_in):
  * tile = 128 residue rows, the three weight matrices resident in shared memory as fp16 (hi, lo) images.
  * wstream = operand images of this layer and path (pp_tc_pre_stream_floats() floats, weights.pack_pre_stream). */

@@ -29,6 +29,7 @@ SIGNATURES = {
     "pp_ipmp_edge_tc": "p" "ii" "ppppp" "iii" "p" "i" "pppp" "ii" "s",
     "pp_ipmp_node_post_tc": "p" "i" "ppp" "iii" "pp" "ii" "s",
     "pp_ipmp_node_pre_tc": "p" "ii" "pp" "ii" "pppp" "s",
+    "pp_ipmp_node_post_tc32": "p" "i" "ppp" "iii" "pp" "s",
     "pp_decode_step": "pp" "ii" "p" "i" "ff" "ppp" "ppp" "f" "s",
     "pp_atom14_fwd": "pppp" "ii" "p" "s",
     "pp_clash_neighbours": "ppppp" "ii" "f" "i" "pppp" "s",
@@ -47,7 +48,7 @@ _lib = None
 
 # kernels launched per entry point (pp_ipmp_layer: 3, or 5 with the edge update - the caller passes `kernels=`)
 KERNELS = {"pp_knn_build": 1, "pp_knn_build_cells": 5, "pp_geometry_build": 1, "pp_edge_embed": 1, "pp_node_embed": 1, "pp_ipmp_layer": 5,
-           "pp_ipmp_node_pre": 1, "pp_ipmp_edge_node": 1, "pp_ipmp_node_post": 1, "pp_ipmp_edge_edge": 1, "pp_ipmp_edge_tc": 1, "pp_ipmp_node_post_tc": 1, "pp_ipmp_node_pre_tc": 1,
+           "pp_ipmp_node_pre": 1, "pp_ipmp_edge_node": 1, "pp_ipmp_node_post": 1, "pp_ipmp_edge_edge": 1, "pp_ipmp_edge_tc": 1, "pp_ipmp_node_post_tc": 1, "pp_ipmp_node_pre_tc": 1, "pp_ipmp_node_post_tc32": 1,
            "pp_decode_step": 1, "pp_atom14_fwd": 1, "pp_clash_neighbours": 1, "pp_clash_reach": 1, "pp_clash_neighbours_cells": 5, "pp_clash_fwd_bwd": 2,
            "pp_prox_init": 4, "pp_prox_step": 3, "pp_prox_init_from_mean": 1, "pp_selftest_umma": 1, "pp_selftest_umma_f16": 1}
 LAUNCHES = 0      # running count of kernels launched through call()

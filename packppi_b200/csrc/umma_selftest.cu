@@ -158,7 +158,7 @@ umma_selftest_f16_kernel(const float* __restrict__ A, const float* __restrict__ 
         float4 y = *reinterpret_cast<const float4*>(A + (size_t)row * K + k0 + u * 8 + 4);
         split_f16x2(x.x, x.y, h.x, l.x); split_f16x2(x.z, x.w, h.y, l.y);
         split_f16x2(y.x, y.y, h.z, l.z); split_f16x2(y.z, y.w, h.w, l.w);
-        if (ts_mode) {
+        if (ts_mode == 1) {
           vh[u * 4] = h.x; vh[u * 4 + 1] = h.y; vh[u * 4 + 2] = h.z; vh[u * 4 + 3] = h.w;
           vl[u * 4] = l.x; vl[u * 4 + 1] = l.y; vl[u * 4 + 2] = l.z; vl[u * 4 + 3] = l.w;
         } else {
@@ -172,7 +172,7 @@ umma_selftest_f16_kernel(const float* __restrict__ A, const float* __restrict__ 
         *reinterpret_cast<uint4*>(b_hi + off) = h;
         *reinterpret_cast<uint4*>(b_lo + off) = l;
       }
-      if (ts_mode) {
+      if (ts_mode == 1) {
         tmem_st16(a_t_hi + lane_base, vh);
         tmem_st16(a_t_lo + lane_base, vl);
         tmem_st_wait();
@@ -182,6 +182,43 @@ umma_selftest_f16_kernel(const float* __restrict__ A, const float* __restrict__ 
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
+    if (ts_mode == 2) {
+      // "promotion": every K = 16 step starts a fresh accumulator (its three passes are the only accumulation the
+      // tensor core does, and two of them are 2^-11 small); the steps are summed in fp32 with round-to-nearest by the
+      // row threads.  Measures what the truncating accumulator costs (tests/test_gpu_umma.py).
+      for (int kk = 0; kk < kSelfKC; kk += 16) {
+        if (tid == 128) {
+          for (int p = 0; p < passes; ++p) {
+            const uint8_t* as = (p == 2) ? a_lo : a_hi;
+            const uint8_t* bs = (p == 1) ? b_lo : b_hi;
+            mma_f16_ss(acc, smem_desc(smem_u32(as) + (kk / 8) * 2048, 2048, 128),
+                       smem_desc(smem_u32(bs) + (kk / 8) * 2048, 2048, 128), idesc, p > 0 ? 1u : 0u);
+          }
+          mma_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        fence_after_sync();
+        if (tid < 128) {
+          const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+#pragma unroll 1
+          for (int c = 0; c < 128; c += 32) {
+            uint32_t v[32];
+            tmem_ld32(acc + lane_base + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float* d = D + (size_t)tid * 128 + c + j;
+              *d = (k0 == 0 && kk == 0) ? __uint_as_float(v[j]) : *d + __uint_as_float(v[j]);
+            }
+          }
+        }
+        fence_before_sync();
+        __syncthreads();
+        fence_after_sync();
+      }
+      continue;
+    }
     if (tid == 128) {
       for (int p = 0; p < passes; ++p) {
         const uint8_t* as = (p == 2) ? a_lo : a_hi;
@@ -191,7 +228,7 @@ umma_selftest_f16_kernel(const float* __restrict__ A, const float* __restrict__ 
         for (int kk = 0; kk < kSelfKC; kk += 16) {
           uint64_t bd = smem_desc(smem_u32(bs) + (kk / 8) * 2048, 2048, 128);
           uint32_t accum = (k0 > 0 || p > 0 || kk > 0) ? 1u : 0u;
-          if (ts_mode) {
+          if (ts_mode == 1) {
             mma_f16_ts(acc, at + kk / 2, bd, idesc, accum);
           } else {
             uint64_t ad = smem_desc(smem_u32(as) + (kk / 8) * 2048, 2048, 128);
@@ -206,7 +243,7 @@ umma_selftest_f16_kernel(const float* __restrict__ A, const float* __restrict__ 
     fence_after_sync();
   }
 
-  if (tid < 128) {
+  if (tid < 128 && ts_mode != 2) {
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
 #pragma unroll 1
     for (int c = 0; c < 128; c += 32) {

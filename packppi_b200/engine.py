@@ -132,22 +132,23 @@ class Engine:
     #   f16x3  tcgen05 tensor cores (kind::f16), every operand split into a rounded fp16 (hi, lo) pair, 3 MMAs per
     #          product, fp32 accumulation: fp32-grade, the parity mode of the tensor path (default)
     #   f16    tensor cores, hi halves only (11 mantissa bits, the precision of TF32): fast mode, looser stated tolerance
-    # node_epilogue: where the per-residue node update (W_out, LayerNorm, FFN 128-512-128, LayerNorm) runs: "ffma" =
-    # exact-fp32 CUDA-core kernel (default of f16x3), "tc" = tensor cores (default of f16).  The tensor core
-    # accumulates in fp32 with truncation (measured bias -7e-7 relative at K = 128, growing linearly with K), which the
-    # h_V path amplifies: against the CPU oracle on fresh inputs (tools/diag_accuracy.py) the max chi error after
-    # 2 / 30 steps is 4.4e-5 / 1.1e-5 rad with "ffma" (fp32 mode: 5.1e-5 / 6.7e-6) but 1.2e-4 / 3.0e-5 with "tc" for
-    # +12 % throughput; the gate is 1e-4 at every step.  The residue prologue (points, A_i, N_j) is accuracy-neutral
-    # on the tensor cores and always runs there in the tensor-core modes.
+    # node_epilogue: where the per-residue node update (W_out, LayerNorm, FFN 128-512-128, LayerNorm) runs:
+    #   "tc32" tensor cores with promoted accumulation (csrc/node_post_tc.cu; default of the tensor-core modes)
+    #   "ffma" exact-fp32 CUDA-core kernel            "tc" tensor cores, plain TMEM accumulation
+    # The tensor core accumulates in fp32 with truncation (measured bias -7e-7 relative at K = 128, growing linearly
+    # with K), which the h_V path amplifies: against the CPU oracle on fresh inputs (tools/diag_accuracy.py) the max
+    # chi error after 2 / 30 steps is 1.2e-4 / 3.0e-5 rad with "tc" (gate: 1e-4 at every step), 4.7e-5 / 9.2e-6 with
+    # "ffma" and 4.5e-5 / 8.3e-6 with "tc32" (fp32 mode: 5.1e-5 / 6.7e-6); throughput 5.93 / 5.30 / 5.81 M.  The
+    # residue prologue (points, A_i, N_j) is accuracy-neutral and always runs on the tensor cores in these modes.
     MODES = ("fp32", "f16x3", "f16")
     ALIASES = {"tf32x3": "f16x3", "tf32": "f16"}   # names of the first tensor-core implementation (split TF32)
 
     def __init__(self, state_dict, device, mode="f16x3", cluster=1, node_epilogue=None):
         mode = self.ALIASES.get(mode, mode)
         if node_epilogue is None:
-            node_epilogue = "tc" if mode == "f16" else "ffma"
-        if node_epilogue not in ("tc", "ffma"):
-            raise ValueError("node_epilogue must be 'tc' or 'ffma'")
+            node_epilogue = "tc32"
+        if node_epilogue not in ("tc", "tc32", "ffma"):
+            raise ValueError("node_epilogue must be 'tc32', 'tc' or 'ffma'")
         self.node_epilogue = node_epilogue
         if mode not in self.MODES:
             raise ValueError(f"mode must be one of {self.MODES}")
@@ -229,9 +230,11 @@ class Engine:
                           ws.wsN, ws.wsP, ws.wsAcc, *tcp, rows=S * G, tag="node")
             if self.mode == "fp32" or self.node_epilogue == "ffma":
                 _lib.call("pp_ipmp_node_post", W, layer, *common, graph.msum, *size, ws.wsAcc, ws.hV, rows=S * G)
+            elif self.node_epilogue == "tc32":
+                _lib.call("pp_ipmp_node_post_tc32", W, layer, self.wtc[layer, 2], graph.msum, graph.mask, G, K, S,
+                          ws.wsAcc, ws.hV, rows=S * G)
             else:
-                # always the 3-pass split, also in the fast mode: h_V feeds every later GEMM of the step and plain
-                # fp16 inputs here would triple the chi error
+                # plain TMEM accumulation; always the 3-pass split, also in the fast mode
                 _lib.call("pp_ipmp_node_post_tc", W, layer, self.wtc[layer, 2], graph.msum, graph.mask, G, K, S,
                           ws.wsAcc, ws.hV, 3, self.cluster, rows=S * G)
             if edge:

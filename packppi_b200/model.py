@@ -86,7 +86,7 @@ class _PackedModule(nn.Module):
     `kernel_mode` selects how the per-edge message MLPs run (engine.Engine.MODES): "fp32" = CUDA-core FFMA (exact),
     "f16x3" = tcgen05 tensor cores with split fp16 operand pairs (fp32-grade, default), "f16" = tensor cores, plain
     fp16 inputs (fast, looser tolerance).  `kernel_cluster` = CTAs per cluster sharing the weight stream in the
-    tensor-core modes (1, 2, 4).  `kernel_node_epilogue` = "tc" | "ffma" | None (mode default): where the per-residue node update runs.
+    tensor-core modes (1, 2, 4).  `kernel_node_epilogue` = "tc32" (default) | "ffma" | "tc": where the per-residue node update runs.
     Defaults come from the environment (PACKPPI_B200_MODE, PACKPPI_B200_CLUSTER, PACKPPI_B200_NODE_EPILOGUE)."""
     kernel_mode = os.environ.get("PACKPPI_B200_MODE", "f16x3")
     kernel_cluster = int(os.environ.get("PACKPPI_B200_CLUSTER", "1"))

@@ -139,3 +139,27 @@ def test_node_pre_tc_matches_cuda_core_kernel(case):
             for name, r, o in zip(("A", "N", "P"), ref, out):
                 scale = max(1.0, r.abs().max().item())
                 assert (r - o).abs().max().item() < 2e-5 * scale, (layer, path, name)
+
+
+@pytest.mark.parametrize("case", ["syn17", "synbatch", "t1124"])
+def test_node_post_tc32_matches_cuda_core_kernel(case):
+    """Node update with promoted (fp32-grade) tensor-core accumulation against the exact fp32 kernel, same inputs."""
+    from packppi_b200 import _lib
+    dev = torch.device("cuda:0")
+    g, b = load_golden(case)
+    bd = b.to(dev)
+    m = _model(dev, "f16x3")
+    eng, graph = m._graph(bd)
+    G, K, S = graph.G, graph.K, 2
+    gen = torch.Generator().manual_seed(3)
+    hV0 = torch.randn(S * G, 128, generator=gen).to(dev)
+    acc = (torch.randn(S * G, 128, generator=gen) * 8.0).to(dev)
+    W = eng.wblob
+    for layer in range(3):
+        ref, out = hV0.clone(), hV0.clone()
+        _lib.call("pp_ipmp_node_post", W, layer, graph.geo, graph.nbr, graph.mask_attend, graph.msum, graph.mask, G, K,
+                  S, acc, ref)
+        _lib.call("pp_ipmp_node_post_tc32", W, layer, eng.wtc[layer, 2], graph.msum, graph.mask, G, K, S, acc, out)
+        torch.cuda.synchronize()
+        assert torch.isfinite(out).all()
+        assert (ref - out).abs().max().item() < 5e-6 * max(1.0, ref.abs().max().item()), layer
