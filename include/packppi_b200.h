@@ -133,6 +133,9 @@ int pp_ipmp_node_pre_tc(const float* weights, int64_t layer, int64_t path, const
 /* Diagnostics: later pp_ipmp_edge_tc launches write clock64() stamps of the phase boundaries of their first tile
  * (CTA 0, one worker thread) into trace (device memory, >= 32 uint64); NULL switches it off. */
 int pp_set_tc_trace(uint64_t* trace);
+/* Which kernel (path 0 = node message, 1 = edge update; default 1) and which tile of CTA 0 (default 0 = the first,
+ * whose stamps include the prologue; for a later tile the stamps start at "G1 complete") the trace records. */
+int pp_set_tc_trace_tile(int64_t path, int64_t it);
 
 /* decoder_score (models/TorsionalDiffusion.py:62-68,106-108) and, if do_step, both SO2VESchedule.step calls in ode
  * mode plus wrap and mask (models/components/schedule.py:198-235, TorsionalDiffusion.py:272-280):
@@ -210,6 +213,11 @@ int pp_selftest_umma(const float* A, const float* W, float* D, int64_t K, int64_
  * fp16 inputs, 3 = split fp16 (~fp32).  ts_mode != 0 feeds A from tensor memory as packed fp16 pairs. */
 int pp_selftest_umma_f16(const float* A, const float* W, float* D, int64_t K, int64_t passes, int64_t ts_mode,
                          pp_stream_t stream);
+
+/* Diagnostics: one TMA gather4 copy (four arbitrary rows of src [rows][128], 32 floats from column col, 128-byte
+ * swizzle, tensor-map box {32, box_rows}); out[256] receives the raw 1 KB of shared memory. */
+int pp_selftest_gather4(const float* src, int64_t rows, int64_t box_rows, int64_t col, int64_t r0, int64_t r1,
+                        int64_t r2, int64_t r3, float* out, pp_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -90,7 +90,8 @@ struct Args {
   const float *rmask, *hres;         // MODE 2: residue mask [G], residual rows h_V [R][128]
   float in_scale;                    // MODE 2: 1 / K applied to the summed messages
   float* out;             // node path: accsum [R][128]; edge path: hE_out [R][K][128]
-  unsigned long long* trace;  // optional: clock64 stamps of CTA 0 / first tile (pp_set_tc_trace), else null
+  unsigned long long* trace;  // optional: clock64 stamps of one tile of CTA 0 (pp_set_tc_trace), else null
+  int trace_it;               // which tile of the CTA (0 = first: the stamps include the prologue)
 };
 
 struct Ring {
@@ -599,12 +600,13 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
     int tile = next_tile((int)blockIdx.x);
     RowCtx cx = row_ctx(tile);
     int qbase = 0;  // first A chunk of the current tile (ring positions persist across tiles)
-    stamp(true);  // 0: start
+    stamp(a.trace_it == 0);  // 0: start
     if (tile < tend) first_operand(cx, 0, R0, true);
-    stamp(true);  // 1: first operand of the first tile published
+    stamp(a.trace_it == 0);  // 1: first operand of the first tile published
 
     for (int it = 0; tile < tend; ++it) {
-      const bool t0 = it == 0;
+      const bool t0 = it == a.trace_it;
+      if (a.trace_it > 0) stamp(t0);  // tile start (a later tile: its first operand was built during the previous one)
       const int nxt_tile = next_tile(tile + tstep);
       const bool more = nxt_tile < tend;
       const int par = EDGE ? (it & 1) : 0;
@@ -652,6 +654,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
       if (!EDGE) {
         // node message path: the next tile's first operand is built while G2 runs; its G1 then overlaps the reduction
         if (more) first_operand(nx, qbase + kChunksTile, 0, true);
+        stamp(t0);  // next first operand published
         mbar_wait(&acc_full[1], accph[1]); accph[1] ^= 1;
         fence_after_sync();
         stamp(t0);  // 4: G2 complete
@@ -931,8 +934,14 @@ using namespace pp;
 extern "C" int64_t pp_tc_stream_floats() { return tc::kStreamFloats; }
 
 static unsigned long long* g_tc_trace = nullptr;
+static int g_tc_trace_it = 0, g_tc_trace_path = 1;
 // Diagnostics: subsequent pp_ipmp_edge_tc launches record clock64() stamps of the first tile of CTA 0 (one worker
 // thread, phase boundaries, see the stamp() calls in edge_tc_kernel) into `trace` (device, >= 32 entries); NULL = off.
+extern "C" int pp_set_tc_trace_tile(int64_t path, int64_t it) {
+  g_tc_trace_path = (int)path;
+  g_tc_trace_it = (int)it;
+  return 0;
+}
 extern "C" int pp_set_tc_trace(uint64_t* trace) {
   g_tc_trace = reinterpret_cast<unsigned long long*>(trace);
   return 0;
@@ -965,7 +974,8 @@ extern "C" int pp_ipmp_edge_tc(const float* weights, int64_t layer, int64_t path
   a.hE_in = hE_in; a.he_shared = (int)he_shared;
   a.A = wsA; a.Nn = wsN; a.pglob = wsP;
   a.out = out;
-  a.trace = path == 1 ? g_tc_trace : nullptr;  // the trace follows the edge-update kernel
+  a.trace = path == g_tc_trace_path ? g_tc_trace : nullptr;  // the trace follows one of the two kernels
+  a.trace_it = g_tc_trace_it;
   int rc;
 #define PP_TC_CASE(E, P, C) if (path == (E) && passes == (P) && cluster == (C)) rc = tc::launch<E, P, C>(a, stream); else
   PP_TC_CASE(0, 3, 1) PP_TC_CASE(0, 3, 2) PP_TC_CASE(0, 3, 4) PP_TC_CASE(0, 1, 1) PP_TC_CASE(0, 1, 2) PP_TC_CASE(0, 1, 4)

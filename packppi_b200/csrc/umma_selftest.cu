@@ -287,3 +287,57 @@ extern "C" int pp_selftest_umma_f16(const float* A, const float* W, float* D, in
   pp::umma_selftest_f16_kernel<<<1, 192, smem, stream>>>(A, W, D, (int)K, (int)passes, (int)ts_mode);
   return pp::check_launch("pp_selftest_umma_f16");
 }
+
+// ---- TMA gather4 probe: four rows of a row-major fp32 matrix [rows][128] -> one 4 x 32-float tile in shared memory
+#include <cuda.h>
+namespace pp {
+__global__ void gather4_probe_kernel(const __grid_constant__ CUtensorMap tm, int col, int r0, int r1, int r2, int r3,
+                                     float* out) {
+  __shared__ __align__(1024) uint8_t tile[1024];
+  __shared__ __align__(8) uint64_t bar;
+  using namespace umma;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) reinterpret_cast<float*>(tile)[i] = -1.f;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&bar, 4 * 128);
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+            smem_u32(tile)),
+        "l"(reinterpret_cast<uint64_t>(&tm)), "r"(smem_u32(&bar)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+        : "memory");
+  }
+  mbar_wait(&bar, 0);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) out[i] = reinterpret_cast<float*>(tile)[i];
+}
+}  // namespace pp
+
+// Diagnostics: gathers rows r[0..3] (32 floats starting at column `col`) of src [rows][128] with one TMA gather4 copy
+// (128-byte swizzle, tensor-map box {32, box_rows}) and returns the raw 1 KB of shared memory in out[256].
+extern "C" int pp_selftest_gather4(const float* src, int64_t rows, int64_t box_rows, int64_t col, int64_t r0, int64_t r1,
+                                   int64_t r2, int64_t r3, float* out, cudaStream_t stream) {
+  PP_REQUIRE(src && out && rows > 0, "bad arguments");
+  using Encode = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return 1;
+  alignas(64) CUtensorMap tm;
+  const cuuint64_t gdim[2] = {128, (cuuint64_t)rows};
+  const cuuint64_t gstr[1] = {512};
+  const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult rc = reinterpret_cast<Encode>(fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(src), gdim, gstr,
+                                             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    snprintf(pp::g_last_error, sizeof(pp::g_last_error), "pp_selftest_gather4: cuTensorMapEncodeTiled failed (%d)", (int)rc);
+    return 1;
+  }
+  pp::gather4_probe_kernel<<<1, 64, 0, stream>>>(tm, (int)col, (int)r0, (int)r1, (int)r2, (int)r3, out);
+  return pp::check_launch("pp_selftest_gather4");
+}

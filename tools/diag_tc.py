@@ -60,6 +60,45 @@ def trace(dev, mode):
         prev = t[i]
 
 
+def trace_big(dev, mode, path, it):
+    """Trace of tile `it` of CTA 0 on a bench-like micro-batch (8 complexes of ~500 residues, 8 samples)."""
+    from packppi_b200 import _lib, synthetic
+    from packppi_b200.batch import collate
+    items = [synthetic.make_complex(c, seed=10 + i) for i, c in enumerate(synthetic.sweep_lengths(8, seed=64))]
+    b = collate(items).to(dev)
+    B, L = b.X.shape[:2]
+    S = 8
+    m = model(dev, mode)
+    eng, graph = m._graph(b)
+    x = ((torch.rand(S, B, L, 4, generator=torch.Generator().manual_seed(1)) * 2 - 1) * 3.14).to(dev).reshape(-1, 4)
+    t = torch.full((S * B * L,), 0.4, device=dev)
+    buf = torch.zeros(64, dtype=torch.int64, device=dev)
+    eng.network(graph, b, x, t)
+    lib = _lib.load()
+    lib.pp_set_tc_trace_tile(ctypes.c_int64(path), ctypes.c_int64(it))
+    lib.pp_set_tc_trace(ctypes.c_void_p(buf.data_ptr()))
+    eng.network(graph, b, x, t)
+    torch.cuda.synchronize()
+    lib.pp_set_tc_trace(None)
+    lib.pp_set_tc_trace_tile(ctypes.c_int64(1), ctypes.c_int64(0))
+    ts = [v for v in buf.cpu().tolist() if v]
+    if path == 0:
+        names = ["tile start", "G1 done", "x1 published", "next first operand", "G2 done", "sums written"]
+    else:
+        names = ["tile start", "G1 done", "x1 published", "G2 done", "x2 published", "G3 done", "e in TMEM"]
+        for j in range(4):
+            names += [f"FFN-in {j} done", f"hidden {j} published"]
+        names += ["next first operand", "FFN-out done", "stored"]
+    print(f"bench-like trace, mode {mode}, {'node message' if path == 0 else 'edge update'}, tile {it} of CTA 0")
+    for i in range(1, min(len(ts), len(names))):
+        print(f"  {names[i]:22s} +{ts[i] - ts[i - 1]:7d}  (total {ts[i] - ts[0]:7d})")
+
+
+if __name__ == "__main__" and os.environ.get("PP_DIAG_BIG"):
+    for p_, it_ in ((1, 5), (1, 20), (0, 5), (0, 20)):
+        trace_big(torch.device("cuda:0"), "f16x3", p_, it_)
+    sys.exit(0)
+
 if __name__ == "__main__":
     dev = torch.device("cuda:0")
     modes = sys.argv[1].split(",") if len(sys.argv) > 1 else ["fp32", "f16x3", "f16"]
