@@ -214,6 +214,18 @@ int pp_selftest_umma(const float* A, const float* W, float* D, int64_t K, int64_
 int pp_selftest_umma_f16(const float* A, const float* W, float* D, int64_t K, int64_t passes, int64_t ts_mode,
                          pp_stream_t stream);
 
+/* Device featurisation of a padded batch [B][L]: restates ComplexDataset.prot_to_data
+ * (src/datamodules/components/complex_dataset.py:64-148), calc_bb_dihedrals / calc_sc_dihedrals (helper.py:39-101)
+ * and the zero padding of collate_fn (complex_datamodule.py:196-226).  Inputs: atom14 coordinates (NaN = missing
+ * atom), residue types, atom masks, chain-offset residue indices, 1-based chain numbers, residue count per complex,
+ * chi tables [21][7] / [21][4] / [21][4].  Outputs: every tensor field of the batch contract, zero in the padding. */
+int pp_featurize(const float* X_in, const int64_t* aatype, const float* atom_mask_in, const int64_t* ridx_in,
+                 const int64_t* chain_in, const int32_t* length, int64_t B, int64_t L, const int32_t* chi_atoms,
+                 const float* chi_mask, const float* chi_pi, float* X, float* atom_mask, int64_t* residue_type,
+                 float* residue_mask, int64_t* residue_index, int64_t* chain_indices, float* bb_d, float* bb_sincos,
+                 float* bb_mask, float* sc_d, float* sc_sincos, float* sc_mask, uint8_t* chi_1pi, uint8_t* chi_2pi,
+                 pp_stream_t stream);
+
 /* Diagnostics: one TMA gather4 copy (four arbitrary rows of src [rows][128], 32 floats from column col, 128-byte
  * swizzle, tensor-map box {32, box_rows}); out[256] receives the raw 1 KB of shared memory. */
 int pp_selftest_gather4(const float* src, int64_t rows, int64_t box_rows, int64_t col, int64_t r0, int64_t r1,

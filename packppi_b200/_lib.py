@@ -39,6 +39,7 @@ SIGNATURES = {
     "pp_prox_init": "ppppppppp" "i" "ff" "p" "pppp" "pp" "ppp" "p" "s",
     "pp_prox_step": "ppppppppp" "ppppp" "i" "ffffffff" "ppp" "ppp" "p" "p" "i" "s",
     "pp_prox_init_from_mean": "pppp" "i" "ppppp" "s",
+    "pp_featurize": "pppppp" "ii" "ppp" "pppppppppppppp" "s",
     "pp_selftest_umma": "ppp" "iii" "s",
     "pp_selftest_umma_f16": "ppp" "iii" "s",
     "pp_selftest_gather4": "p" "iiiiiii" "p" "s",
@@ -51,7 +52,7 @@ _lib = None
 KERNELS = {"pp_knn_build": 1, "pp_knn_build_cells": 5, "pp_geometry_build": 1, "pp_edge_embed": 1, "pp_node_embed": 1, "pp_ipmp_layer": 5,
            "pp_ipmp_node_pre": 1, "pp_ipmp_edge_node": 1, "pp_ipmp_node_post": 1, "pp_ipmp_edge_edge": 1, "pp_ipmp_edge_tc": 1, "pp_ipmp_node_post_tc": 1, "pp_ipmp_node_pre_tc": 1, "pp_ipmp_node_post_tc32": 1,
            "pp_decode_step": 1, "pp_atom14_fwd": 1, "pp_clash_neighbours": 1, "pp_clash_reach": 1, "pp_clash_neighbours_cells": 5, "pp_clash_fwd_bwd": 2,
-           "pp_prox_init": 4, "pp_prox_step": 3, "pp_prox_init_from_mean": 1, "pp_selftest_umma": 1, "pp_selftest_umma_f16": 1, "pp_selftest_gather4": 1}
+           "pp_prox_init": 4, "pp_prox_step": 3, "pp_prox_init_from_mean": 1, "pp_featurize": 1, "pp_selftest_umma": 1, "pp_selftest_umma_f16": 1, "pp_selftest_gather4": 1}
 LAUNCHES = 0      # running count of kernels launched through call()
 PROFILE = None    # {entry name: []} -> call() appends (start event, end event, rows) around those entries
 

@@ -3,7 +3,7 @@
 Restates `ComplexDataset.prot_to_data` (reference src/datamodules/components/complex_dataset.py:64-148),
 `calc_dihedrals / calc_bb_dihedrals / calc_sc_dihedrals` (src/datamodules/components/helper.py:20-101) and
 `ProteinAnalysis.get_prot` (src/utils/protein_analysis.py:103-122, minus the interface mask).  It defines the
-batch contract the kernels consume; SURVEY.md §8(f) row 1 lists a device version as the next step.
+batch contract the kernels consume; `proteins_to_batch_device` is the device version.
 """
 import numpy as np
 import torch
@@ -64,6 +64,69 @@ def chain_codes(chain_id):
     return np.asarray(out, np.int64)
 
 
+def offset_residue_index(ridx, chain):
+    """complex_dataset.py:86-92: running offset = max index of the previous chains + 100 (ridx is modified)."""
+    uniq = torch.unique(chain)
+    if len(uniq) > 1:
+        off = 0
+        for c in uniq[:-1]:
+            off += int(ridx[chain == c].max())
+            off += 100
+            ridx[chain == c + 1] += off
+    return ridx
+
+
+_DEV_TABLES = {}
+
+
+def proteins_to_batch_device(proteins, device):
+    """The same batch as collate([protein_to_batch(p) for p in proteins]).to(device), featurised ON the device
+    (csrc/featurize.cu): the raw atom records are padded on the host, copied once, and one kernel
+    writes every field.  Angles agree with the host version to fp32 rounding of the dihedral arithmetic (the acos near
+    a planar angle amplifies it: up to ~1e-4 rad there), masks and integer fields exactly."""
+    from . import _lib
+    device = torch.device(device)
+    t = tables.raw()
+    B = len(proteins)
+    lens = [int(np.asarray(p["aaindex"]).shape[0]) for p in proteins]
+    L = max(lens)
+    X = np.zeros((B, L, 14, 3), np.float32)
+    aa = np.zeros((B, L), np.int64)
+    am = np.zeros((B, L, 14), np.float32)
+    ri = np.zeros((B, L), np.int64)
+    ch = np.zeros((B, L), np.int64)
+    for b, p in enumerate(proteins):
+        n = lens[b]
+        X[b, :n] = np.asarray(p["atom_positions"], np.float32)
+        aa[b, :n] = np.asarray(p["aaindex"], np.int64)
+        am[b, :n] = np.asarray(p["atom_mask"], np.float32)
+        chain = torch.from_numpy(chain_codes(p["chain_id"]))
+        ridx = offset_residue_index(torch.from_numpy(np.asarray(p["residue_index"])).to(torch.int64).clone(), chain)
+        ri[b, :n] = ridx.numpy()
+        ch[b, :n] = chain.numpy()
+    if device not in _DEV_TABLES:
+        _DEV_TABLES[device] = (torch.from_numpy(t["chi_atom_indices_atom14"].astype(np.int32)).to(device).contiguous(),
+                               torch.from_numpy(t["chi_mask_atom14"].astype(np.float32)).to(device).contiguous(),
+                               torch.from_numpy(t["chi_pi_periodic"].astype(np.float32)).to(device).contiguous())
+    up = lambda a: torch.from_numpy(a).to(device)  # noqa: E731
+    f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=device)  # noqa: E731
+    i64 = lambda *s: torch.empty(*s, dtype=torch.int64, device=device)  # noqa: E731
+    u8 = lambda *s: torch.empty(*s, dtype=torch.uint8, device=device)  # noqa: E731
+    out = ComplexBatch(X=f32(B, L, 14, 3), atom_mask=f32(B, L, 14), residue_type=i64(B, L), residue_mask=f32(B, L),
+                       residue_index=i64(B, L), chain_indices=i64(B, L), BB_D=f32(B, L, 3), BB_D_sincos=f32(B, L, 3, 2),
+                       BB_D_mask=f32(B, L, 3), SC_D=f32(B, L, 4), SC_D_sincos=f32(B, L, 4, 2), SC_D_mask=f32(B, L, 4),
+                       chi_1pi_periodic_mask=u8(B, L, 4), chi_2pi_periodic_mask=u8(B, L, 4))
+    _lib.call("pp_featurize", up(X), up(aa), up(am), up(ri), up(ch), torch.tensor(lens, dtype=torch.int32, device=device),
+              B, L, *_DEV_TABLES[device], *[out[k] for k in ("X", "atom_mask", "residue_type", "residue_mask",
+                                                             "residue_index", "chain_indices", "BB_D", "BB_D_sincos",
+                                                             "BB_D_mask", "SC_D", "SC_D_sincos", "SC_D_mask",
+                                                             "chi_1pi_periodic_mask", "chi_2pi_periodic_mask")])
+    out["chi_1pi_periodic_mask"] = out["chi_1pi_periodic_mask"].bool()
+    out["chi_2pi_periodic_mask"] = out["chi_2pi_periodic_mask"].bool()
+    out["num_nodes"], out["num_proteins"], out["max_size"] = L, B, L
+    return out
+
+
 def protein_to_batch(protein):
     """dict(atom_positions[L,14,3], aaindex[L], atom_mask[L,14], residue_index[L], chain_id[L]) -> batch of one.
 
@@ -77,13 +140,7 @@ def protein_to_batch(protein):
     ridx = torch.from_numpy(np.asarray(protein["residue_index"])).to(torch.int64).clone()
     chain = torch.from_numpy(chain_codes(protein["chain_id"]))
 
-    uniq = torch.unique(chain)
-    if len(uniq) > 1:  # complex_dataset.py:86-92: running offset = max index of the previous chains + 100
-        off = 0
-        for c in uniq[:-1]:
-            off += int(ridx[chain == c].max())
-            off += 100
-            ridx[chain == c + 1] += off
+    ridx = offset_residue_index(ridx, chain)
 
     rmask = torch.isfinite(X[:, :4].sum(dim=(-1, -2))).float()
     BB_D, BB_m = calc_bb_dihedrals(X, ridx)
