@@ -61,7 +61,7 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,enforced.power.limit")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
@@ -100,7 +100,7 @@ class ClockSampler:
         """Summary of the samples taken between two time.monotonic() stamps."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, pw, plim = [], None, set(), [], None
         for ts, r in list(self.rows):
             if ts < t0 or ts > t1:
                 continue
@@ -109,11 +109,17 @@ class ClockSampler:
                 mx = float(r[2])
             except (ValueError, IndexError):
                 continue
+            try:
+                pw.append(float(r[3]))
+                plim = float(r[8])
+            except (ValueError, IndexError):
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None,
-                "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+                "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w": statistics.median(pw) if pw else None, "power_limit_w": plim}
 
 
 def build_sweep(n_complexes, seed_base, rank):
