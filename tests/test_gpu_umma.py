@@ -42,3 +42,22 @@ def test_umma_tile_f16(K, ts_mode, passes):
     scale = ref.abs().max().item()
     # plain fp16 keeps 11 bits of each input; the rounded (hi, lo) pairs keep 22
     assert err < (2e-6 if passes == 3 else 3e-3) * max(scale, 1.0) * (K / 32) ** 0.5, (err, scale)
+
+
+def test_tma_gather4_semantics():
+    """cp.async.bulk.tensor.2d ... tile::gather4 with a tensor-map box of {32 floats, 1 row} and 128-byte swizzle:
+    four arbitrary rows land as four consecutive 128-byte rows, 16-byte unit u of shared-memory row r at
+    r * 128 + ((u ^ (r & 7)) << 4) - the layout the staged tiles of csrc/mpnn_tc.cu use."""
+    from packppi_b200 import _lib
+    dev = torch.device("cuda:0")
+    src = torch.arange(64 * 128, dtype=torch.float32, device=dev).reshape(64, 128)
+    out = torch.zeros(256, device=dev)
+    rows, col = (5, 17, 2, 9), 32
+    _lib.call("pp_selftest_gather4", src, 64, 1, col, *rows, out)
+    torch.cuda.synchronize()
+    o = out.cpu().reshape(8, 8, 4)
+    for r, srow in enumerate(rows):
+        for u in range(8):
+            want = src[srow, col + 4 * u:col + 4 * u + 4].cpu()
+            assert torch.equal(o[r, u ^ (r & 7)], want), (r, u)
+    assert bool((o[4:] == -1).all())
