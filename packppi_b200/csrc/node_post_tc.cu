@@ -28,6 +28,13 @@ namespace post {
 using namespace umma;
 
 constexpr int kRows = 128, kKC = 32, kSA = 4, kSB = 4;
+#ifndef PP_POST_PROMOTE
+#define PP_POST_PROMOTE 2
+#endif
+// K = 16 steps accumulated in TMEM before the row threads take the partial sum over (1, 2 or 4): every hand-off is a
+// round trip between the MMA warp and 256 threads, every extra step one more truncated accumulation
+constexpr int kPromote = PP_POST_PROMOTE;
+static_assert(kPromote == 1 || kPromote == 2 || kPromote == 4, "promotion interval");
 constexpr uint32_t kImgBytes = kRows * kKC * 2;
 constexpr uint32_t kSlotBytes = 2 * kImgBytes;
 constexpr uint32_t kLbo = kRows * 16, kSbo = 128;
@@ -131,7 +138,8 @@ __global__ void __launch_bounds__(kThreads, 1) node_post_tc_kernel(const Args a)
     constexpr uint32_t kHi = desc_hi(kSbo);
     int ia = 0, ib = 0;
     uint32_t pa = 0, pb = 0, pe = 0;
-    uint32_t t = 0;  // K = 16 steps issued so far: buffer t & 1, use number t >> 1 of that buffer
+    uint32_t t = 0;  // promoted groups issued so far: buffer t & 1, use number t >> 1 of that buffer
+    int sub = 0;     // K = 16 steps already accumulated in the current group
     // one 32-column chunk = two promoted steps; ss: A from the ring, else from TMEM at a_tm (packed, lo at + 64)
     auto chunk = [&](bool ss, uint32_t a_tm) {
       if (ss) mbar_wait(&a_full[ia], pa);
@@ -142,25 +150,29 @@ __global__ void __launch_bounds__(kThreads, 1) node_post_tc_kernel(const Args a)
 #pragma unroll
       for (int kk = 0; kk < kKC; kk += 16) {
         const uint32_t buf = t & 1;
-        mbar_wait(&step_free[buf], ((t >> 1) & 1) ^ 1);
-        fence_after_sync();
+        if (sub == 0) {
+          mbar_wait(&step_free[buf], ((t >> 1) & 1) ^ 1);
+          fence_after_sync();
+        }
+        const bool last = sub + 1 == kPromote;
         if (elect_one_sync()) {
           const uint32_t acc = buf ? BUF1 : BUF0;
 #pragma unroll
           for (int p = 0; p < 3; ++p) {
             const uint32_t ad = (((p == 2) ? kImgBytes : 0u) + (kk / 8) * kLbo) >> 4;
             const uint32_t bd = (((p == 1) ? kImgBytes : 0u) + (kk / 8) * kLbo) >> 4;
-            if (ss) mma_f16_ss2(acc, a_lo + ad, b_lo + bd, kHi, kIdesc, p > 0);
-            else mma_f16_ts2(acc, a_tm + ((p == 2) ? 64 : 0) + kk / 2, b_lo + bd, kHi, kIdesc, p > 0);
+            const uint32_t accum = (sub > 0 || p > 0) ? 1u : 0u;
+            if (ss) mma_f16_ss2(acc, a_lo + ad, b_lo + bd, kHi, kIdesc, accum);
+            else mma_f16_ts2(acc, a_tm + ((p == 2) ? 64 : 0) + kk / 2, b_lo + bd, kHi, kIdesc, accum);
           }
-          mma_commit(&step_full[buf]);
+          if (last) mma_commit(&step_full[buf]);
           if (kk == 16) {
             mma_commit(&b_empty[ib]);
             if (ss) mma_commit(&a_empty[ia]);
           }
         }
         __syncwarp();
-        ++t;
+        if (last) { sub = 0; ++t; } else { ++sub; }
       }
       if (++ib == kSB) { ib = 0; pb ^= 1; }
       if (ss && ++ia == kSA) { ia = 0; pa ^= 1; }
@@ -193,10 +205,10 @@ __global__ void __launch_bounds__(kThreads, 1) node_post_tc_kernel(const Args a)
       fence_async_smem();
       mbar_arrive(&a_full[slot]);
     };
-    // add the eight K = 16 steps of one K = 128 product into acc (this thread's 2 x 32 columns)
+    // add the 8 / kPromote partial sums of one K = 128 product into acc (this thread's 2 x 32 columns)
     auto drain = [&](float (&acc)[2][32]) {
 #pragma unroll 1
-      for (int s = 0; s < 8; ++s, ++t) {
+      for (int s = 0; s < 8 / kPromote; ++s, ++t) {
         const uint32_t buf = t & 1;
         mbar_wait(&step_full[buf], (t >> 1) & 1);
         fence_after_sync();
