@@ -205,7 +205,8 @@ int pp_prox_init_from_mean(const float* per_res, const float* mean, const float*
                            uint8_t* mask, float* z, float* x, float* m, float* v, pp_stream_t stream);
 
 /* Diagnostics: one 128 x 128 tile D = A W^T on the tcgen05 tensor cores (A [128][K], W [128][K], K % 32 == 0),
- * passes 1 = TF32, 3 = split TF32 (~fp32); ts_mode != 0 feeds A from tensor memory instead of shared memory.
+ * (kind::tf32: the first tensor-core implementation, kept as a probe) passes 1 = TF32, 3 = split TF32 (~fp32);
+ * ts_mode != 0 feeds A from tensor memory instead of shared memory.
  * Pins the descriptor encodings the fused tensor-core kernels rely on (tests/test_gpu_umma.py). */
 int pp_selftest_umma(const float* A, const float* W, float* D, int64_t K, int64_t passes, int64_t ts_mode,
                      pp_stream_t stream);

@@ -174,9 +174,8 @@ def test_sde_sampling_with_injected_noise(dev):
     m = m.to(dev).eval()
     out = m.sampling(b.to(dev), init_SC_D=tt(g["in_SC_D_init"]).to(dev), sde_noise=tt(g["in_sde_noise"]).to(dev))
     d = wrapped_diff(out.cpu(), tt(g["ref_SC_D_final"]))
-    # the SDE doubles the drift and injects noise of size g sqrt(dt) every step: rounding differences grow ~10x faster
-    # than along the ODE (fp32 FFMA kernels end within 1.4e-5 rad, split TF32 within 1.7e-4 rad, mean 3e-5)
-    assert d.max().item() < 3e-4 and d.mean().item() < 5e-5, (d.max().item(), d.mean().item())
+    # measured: 1.8e-5 rad max in the default tensor-core mode, 1.4e-5 with the fp32 CUDA-core kernels
+    assert d.max().item() < CHI_TOL, (d.max().item(), d.mean().item())
     m.kernel_mode = "fp32"
     out32 = m.sampling(b.to(dev), init_SC_D=tt(g["in_SC_D_init"]).to(dev), sde_noise=tt(g["in_sde_noise"]).to(dev))
     assert wrapped_diff(out32.cpu(), tt(g["ref_SC_D_final"])).max().item() < CHI_TOL
