@@ -211,7 +211,9 @@ int pp_prox_init_from_mean(const float* per_res, const float* mean, const float*
 int pp_selftest_umma(const float* A, const float* W, float* D, int64_t K, int64_t passes, int64_t ts_mode,
                      pp_stream_t stream);
 /* Same tile through kind::f16 with fp16 (hi, lo) operand pairs (the format the fused kernels use): passes 1 = plain
- * fp16 inputs, 3 = split fp16 (~fp32).  ts_mode != 0 feeds A from tensor memory as packed fp16 pairs. */
+ * fp16 inputs, 3 = split fp16 (~fp32).  ts_mode 1 feeds A from tensor memory as packed fp16 pairs; ts_mode 2 starts
+ * a fresh accumulator for every K = 16 step and sums the steps in fp32 with round-to-nearest ("promotion", the scheme
+ * of pp_ipmp_node_post_tc32), which removes the bias of the tensor core's truncating fp32 accumulation. */
 int pp_selftest_umma_f16(const float* A, const float* W, float* D, int64_t K, int64_t passes, int64_t ts_mode,
                          pp_stream_t stream);
 

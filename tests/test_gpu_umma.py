@@ -61,3 +61,23 @@ def test_tma_gather4_semantics():
             want = src[srow, col + 4 * u:col + 4 * u + 4].cpu()
             assert torch.equal(o[r, u ^ (r & 7)], want), (r, u)
     assert bool((o[4:] == -1).all())
+
+
+def test_tensor_core_accumulation_truncates_and_promotion_fixes_it():
+    """The finding behind csrc/node_post_tc.cu: accumulating a long all-positive sum in TMEM is biased low (the fp32
+    accumulator truncates), starting a fresh accumulator every K = 16 and summing in fp32 registers is not."""
+    from packppi_b200 import _lib
+    dev = torch.device("cuda:0")
+    K = 512
+    g = torch.Generator().manual_seed(K)
+    A = (torch.rand(128, K, generator=g) + 0.5).to(dev)
+    W = (torch.rand(128, K, generator=g) + 0.5).to(dev)
+    ref = A.double() @ W.double().t()
+    bias = {}
+    for name, ts in (("tmem", 0), ("promoted", 2)):
+        D = torch.zeros(128, 128, device=dev)
+        _lib.call("pp_selftest_umma_f16", A, W, D, K, 3, ts)
+        torch.cuda.synchronize()
+        bias[name] = ((D.double() - ref) / ref).mean().item()
+    assert bias["tmem"] < -2e-6, bias          # measured -3.4e-6 at K = 512 (-7e-7 at K = 128)
+    assert abs(bias["promoted"]) < 3e-7, bias  # measured -1.0e-7 (the 22-bit operand split)
