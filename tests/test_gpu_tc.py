@@ -163,3 +163,24 @@ def test_node_post_tc32_matches_cuda_core_kernel(case):
         torch.cuda.synchronize()
         assert torch.isfinite(out).all()
         assert (ref - out).abs().max().item() < 5e-6 * max(1.0, ref.abs().max().item()), layer
+
+
+@pytest.mark.parametrize("node_epilogue", ["tc32", "tc", "ffma"])
+def test_node_epilogue_options(node_epilogue):
+    """The three homes of the per-residue node update: promoted tensor-core accumulation (default), plain TMEM
+    accumulation (MODE 2 of edge_tc_kernel) and the CUDA-core kernel, all within the activation gate of one network
+    evaluation; only "tc" misses the 1e-4 rad gate after the first ODE steps (tools/diag_accuracy.py)."""
+    from packppi_b200 import TDiffusionModule, weights
+    dev = torch.device("cuda:0")
+    g, b = load_golden("t1124")
+    bd = b.to(dev)
+    B, L = b.X.shape[:2]
+    m = TDiffusionModule()
+    m.load_state_dict(weights.make_state_dict(0))
+    m.kernel_mode, m.kernel_node_epilogue = "f16x3", node_epilogue
+    m = m.to(dev).eval()
+    assert m.engine(dev).node_epilogue == node_epilogue
+    score, hV = m.network(bd, tt(g["in_probe_SC_D"]).to(dev), torch.full((B * L,), 0.7, device=dev))
+    torch.cuda.synchronize()
+    assert (hV.cpu() - tt(g["ref_probe_hV"])).abs().max().item() < TOL["f16x3"]["act"]
+    assert (score.cpu() - tt(g["ref_probe_score"])).abs().max().item() < TOL["f16x3"]["act"]
