@@ -191,6 +191,12 @@ def workload_config(args):
                         "BASELINE.json configs[4]",
             "weights": "random init, packppi_b200.weights.make_state_dict(0)", "samples_per_complex": N_SAMPLES,
             "denoise_steps": N_ODE, "l2": "per-micro-batch h_E working set 0.3-1.6 GB > 126 MB L2 (inputs larger than L2)",
+            "arithmetic": {"f16x3": "fp32-grade: every product is 3 tcgen05 fp16 MMAs on rounded (hi, lo) operand pairs "
+                                    "with fp32 accumulation, the node update with promoted fp32 sums; meets the fp32 "
+                                    "parity gates (chi <= 1e-4 rad at every step against the reference)",
+                           "fp32": "fp32 FFMA on CUDA cores",
+                           "f16": "fast mode: plain fp16 tensor-core inputs, fp32 accumulation (own tolerance 2e-2 rad)"
+                           }.get(os.environ.get("PACKPPI_B200_MODE", "f16x3"), "see kernel_mode"),
             "parallelism": "one sweep per GPU, no data-path collective"}
 
 
