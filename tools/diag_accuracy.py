@@ -23,11 +23,23 @@ def main():
         models[(mode, ne)] = m.to(dev).eval()
     worst = {c: [0.0, 0.0] for c in configs}
     for seed in range(int(sys.argv[1]) if len(sys.argv) > 1 else 6):
-        b = synthetic.make_complex((40 + 3 * seed, 24 + seed), seed=seed, place_side_chains=po.atom14_coords)
+        scale = int(os.environ.get("PP_DIAG_SCALE", "1"))  # PP_DIAG_SCALE=4: complexes of 256-340 residues
+        b = synthetic.make_complex((scale * (40 + 3 * seed), scale * (24 + seed)), seed=seed,
+                                   place_side_chains=po.atom14_coords)
         L = b.X.shape[1]
         g = torch.Generator().manual_seed(100 + seed)
         x0 = ((torch.rand(1, L, 4, generator=g) * 2 - 1) * 3.14159) * b.SC_D_mask
         refs = {n: mo.sampling(sd, b, x0, n_steps=n) for n in (2, 30)}
+        # The inter-residue dihedral features are raw signed angles: at exactly planar / degenerate geometry
+        # (|cos| rounding past 1 -> NaN -> 0 in the reference, or an angle at +-pi) a 1-ulp difference moves the
+        # feature by pi or 2 pi and the edge embedding of that edge by O(1).  Ideal synthetic backbones hit that on some
+        # seeds; such a complex is reported, not scored (deviation 2).
+        E_idx = mo.knn_graph(b.X[:, :, 1, :], b.residue_mask)[1]
+        hE_ref = mo.edge_embedding(sd, b, E_idx)
+        _, graph0 = models[configs[0]]._graph(b.to(dev))
+        dE = (graph0.hE0.cpu().reshape(hE_ref.shape) - hE_ref).abs().amax(-1)[0]
+        self_edge = E_idx[0] == torch.arange(L).view(-1, 1)
+        degenerate = int(((dE > 1e-2) & ~self_edge).sum())
         bd = b.to(dev)
         line = [f"seed {seed} L {L:3d}"]
         for c in configs:
@@ -36,8 +48,11 @@ def main():
                 chi = eng.sample(graph, bd, x0.reshape(-1, 4).to(dev), n_steps=n).cpu().reshape(1, L, 4)
                 d = (chi - refs[n]).abs()
                 d = torch.minimum(d, 2 * 3.141592653589793 - d).max().item()
-                worst[c][i] = max(worst[c][i], d)
+                if not degenerate:
+                    worst[c][i] = max(worst[c][i], d)
                 line.append(f"{c[0]}/{c[1]} n={n}: {d:.1e}")
+        if degenerate:
+            line.append(f"[{degenerate} degenerate dihedral feature(s): not scored]")
         print("  ".join(line), flush=True)
     for c in configs:
         print(f"worst {c[0]}/{c[1]}: 2 steps {worst[c][0]:.2e}, 30 steps {worst[c][1]:.2e}")
