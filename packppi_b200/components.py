@@ -41,11 +41,17 @@ _ctx_cache = {}
 
 
 def clash_context(batch, violation_tolerance_factor=12., clash_overlap_tolerance=0.5):
-    """Static neighbour list / tables for `batch`, cached while the same tensors are passed again."""
-    key = (batch.X.data_ptr(), batch.atom_mask.data_ptr(), batch.residue_index.data_ptr(), tuple(batch.X.shape),
-           float(violation_tolerance_factor), float(clash_overlap_tolerance))
+    """Static neighbour list / tables for `batch`, cached while the same tensors are passed again.
+
+    The key holds the tensors themselves (identity + version counter): data pointers are recycled by the allocator as
+    soon as a batch is freed, so a pointer key would serve the neighbour list of the previous complex to the next one
+    of the same size."""
+    tensors = (batch.X, batch.residue_type, batch.atom_mask, batch.residue_index)
+    key = (tensors, tuple(t._version for t in tensors), float(violation_tolerance_factor),
+           float(clash_overlap_tolerance))
     hit = _ctx_cache.get("ctx")
-    if hit is None or hit[0] != key:
+    same = (hit is not None and hit[0][1:] == key[1:] and all(a is b for a, b in zip(hit[0][0], key[0])))
+    if not same:
         ctx = ClashContext(batch.X.device, batch.X, batch.residue_type, batch.atom_mask, batch.residue_index,
                            violation_tolerance_factor, clash_overlap_tolerance)
         _ctx_cache["ctx"] = (key, ctx)

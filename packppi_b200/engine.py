@@ -141,6 +141,7 @@ class Engine:
     # "ffma" and 4.5e-5 / 8.3e-6 with "tc32" (fp32 mode: 5.1e-5 / 6.7e-6); throughput 5.93 / 5.30 / 5.81 M.  The
     # residue prologue (points, A_i, N_j) is accuracy-neutral and always runs on the tensor cores in these modes.
     MODES = ("fp32", "f16x3", "f16")
+    _serial = 0
     ALIASES = {"tf32x3": "f16x3", "tf32": "f16"}   # names of the first tensor-core implementation (split TF32)
 
     def __init__(self, state_dict, device, mode="f16x3", cluster=1, node_epilogue=None):
@@ -153,6 +154,9 @@ class Engine:
         if mode not in self.MODES:
             raise ValueError(f"mode must be one of {self.MODES}")
         self.mode, self.cluster = mode, int(cluster)
+        Engine._serial += 1
+        self.serial = Engine._serial  # identifies this set of packed weights (keys of captured CUDA graphs); not id():
+        #                               ids are recycled when an engine is rebuilt after a weight update
         self.dev = torch.device(device)
         if self.dev.type != "cuda":
             raise RuntimeError("packppi_b200 runs on CUDA devices only; there is no CPU fallback "
@@ -322,7 +326,7 @@ class Engine:
             self._run_steps(graph, self.workspace(G, K, S), ni, step_mask, chi, tvals, coefs, trajectory,
                             sde=(m1, sde_noise.to(self.dev, torch.float32).contiguous()))
             return chi
-        key = (S, n_steps, float(annealed_temp), self.mode, self.cluster, id(self))
+        key = (S, n_steps, float(annealed_temp), self.mode, self.cluster, self.serial)
         small = S * G <= GRAPH_ROWS_MAX and trajectory is None and _lib.PROFILE is None and GRAPH_ROWS_MAX > 0
         if not small or (key not in graph._seen and key not in graph._replay):
             graph._seen.add(key)

@@ -234,10 +234,18 @@ class TDiffusionModule(_PackedModule):
         return model
 
     def _graph(self, batch):
-        """Graph + edge embedding of `batch`, reused while the same batch object (and weights) is passed again."""
+        """Graph + edge embedding of `batch`, reused while the same tensors (and weights) are passed again.
+
+        The cache key holds the tensors that define the graph themselves (identity + version counter), not `id()`s or
+        data pointers: both are recycled as soon as a batch is freed, and a recycled key once served the graph of a
+        5-residue complex to a 17-residue one."""
         eng = self.engine(batch.X.device)
-        key = (id(batch), batch.X.data_ptr(), getattr(self, "_engine_sig", None))
-        if self._graph_cache[0] != key:
+        tensors = (batch.X, batch.residue_mask, batch.residue_index, batch.chain_indices)
+        key = (tensors, tuple(t._version for t in tensors), getattr(self, "_engine_sig", None))
+        old = self._graph_cache[0]
+        same = (old is not None and old[2] == key[2] and old[1] == key[1]
+                and all(a is b for a, b in zip(old[0], key[0])))
+        if not same:
             prev = self._graph_cache[1]
             if prev is not None and (prev.B, prev.L) != tuple(batch.X.shape[:2]):
                 prev = None

@@ -436,3 +436,33 @@ def test_tiny_and_ragged_inputs_match_oracle(name, model, dev):
     ref = mo.sampling(weights.make_state_dict(0), b, x0[0], n_steps=30)
     assert wrapped_diff(out[0], ref).max().item() < CHI_TOL
     assert torch.equal(out * b.SC_D_mask, out)
+
+
+def test_caches_survive_recycled_batch_memory(dev):
+    """Graph and clash-context caches must key on the tensors themselves: a freed batch's id() and device pointers are
+    recycled by the next batch of the same shape (regression: a recycled key served a stale graph)."""
+    from packppi_b200 import TDiffusionModule, compute_residue_clash, synthetic, weights
+
+    def fresh_model():
+        m = TDiffusionModule()
+        m.load_state_dict(weights.make_state_dict(0))
+        return m.to(dev).eval()
+
+    model = fresh_model()
+    init = ((torch.rand(1, 33, 4, generator=torch.Generator().manual_seed(3)) * 2 - 1) * math.pi)
+    outs, clashes, ptrs = [], [], []
+    for seed in (1, 2, 3):
+        b = synthetic.make_complex((20, 13), seed=seed).to(dev)
+        ptrs.append(b.X.data_ptr())
+        outs.append(model.sampling(b, init_SC_D=(init * b.SC_D_mask.cpu()).to(dev)).cpu())
+        clashes.append(compute_residue_clash(b, b.SC_D).cpu())
+        del b  # frees the tensors: the next batch of the same shape gets the same addresses
+    for i, seed in enumerate((1, 2, 3)):
+        b = synthetic.make_complex((20, 13), seed=seed).to(dev)
+        ref = fresh_model().sampling(b, init_SC_D=(init * b.SC_D_mask.cpu()).to(dev)).cpu()
+        assert torch.equal(outs[i], ref), seed
+        from packppi_b200 import components
+        components._ctx_cache.clear()
+        assert torch.equal(clashes[i], compute_residue_clash(b, b.SC_D).cpu()), seed
+    # the scenario really happened in this run (informational: allocator behaviour is not guaranteed)
+    print("recycled X pointers:", len(set(ptrs)) < len(ptrs))
