@@ -184,3 +184,37 @@ def test_node_epilogue_options(node_epilogue):
     torch.cuda.synchronize()
     assert (hV.cpu() - tt(g["ref_probe_hV"])).abs().max().item() < TOL["f16x3"]["act"]
     assert (score.cpu() - tt(g["ref_probe_score"])).abs().max().item() < TOL["f16x3"]["act"]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_shapes_tensor_cores_match_cuda_cores(seed):
+    """Shape fuzz: ragged batches of 1-3 complexes of 4-70 residues, 1-4 samples (tiles that straddle samples and
+    complexes, K < 32, partial last tiles); one network evaluation, tensor-core mode against the exact fp32 kernels."""
+    import random
+    from packppi_b200 import TDiffusionModule, synthetic, weights
+    from packppi_b200.batch import collate
+    rnd = random.Random(1000 + seed)
+    dev = torch.device("cuda:0")
+    items = []
+    for i in range(rnd.randint(1, 3)):
+        n = rnd.randint(4, 70)
+        a = rnd.randint(2, n - 2)
+        items.append(synthetic.make_complex((a, n - a), seed=seed * 10 + i))
+    b = collate(items).to(dev)
+    B, L = b.X.shape[:2]
+    S = rnd.randint(1, 4)
+    x = ((torch.rand(S, B, L, 4, generator=torch.Generator().manual_seed(seed)) * 2 - 1) * 3.14).to(dev)
+    t = torch.full((S * B * L,), 0.3 + 0.1 * seed, device=dev)
+    res = {}
+    for mode in ("fp32", "f16x3"):
+        m = TDiffusionModule()
+        m.load_state_dict(weights.make_state_dict(0))
+        m.kernel_mode = mode
+        m = m.to(dev).eval()
+        eng, graph = m._graph(b)
+        score, hV = eng.network(graph, b, x.reshape(-1, 4).contiguous(), t)
+        torch.cuda.synchronize()
+        res[mode] = (score.clone(), hV.clone())
+    assert torch.isfinite(res["f16x3"][1]).all()
+    assert (res["fp32"][1] - res["f16x3"][1]).abs().max().item() < TOL["f16x3"]["act"], (B, L, S)
+    assert (res["fp32"][0] - res["f16x3"][0]).abs().max().item() < TOL["f16x3"]["act"], (B, L, S)
