@@ -76,9 +76,21 @@ def trace_big(dev, mode, path, it):
     eng.network(graph, b, x, t)
     lib = _lib.load()
     lib.pp_set_tc_trace_tile(ctypes.c_int64(path), ctypes.c_int64(it))
-    lib.pp_set_tc_trace(ctypes.c_void_p(buf.data_ptr()))
+    layer_sel = int(os.environ.get("PP_DIAG_LAYER", "-1"))  # trace only this layer's launch (-1: the last one wins)
+    orig_call = _lib.call
+
+    def traced_call(name, *args, **kw):
+        if name == "pp_ipmp_edge_tc":
+            on = layer_sel < 0 or args[1] == layer_sel
+            lib.pp_set_tc_trace(ctypes.c_void_p(buf.data_ptr()) if on else None)
+        return orig_call(name, *args, **kw)
+
+    _lib.call = traced_call
+    import packppi_b200.engine as _eng
+    _eng._lib.call = traced_call
     eng.network(graph, b, x, t)
     torch.cuda.synchronize()
+    _lib.call = orig_call
     lib.pp_set_tc_trace(None)
     lib.pp_set_tc_trace_tile(ctypes.c_int64(1), ctypes.c_int64(0))
     ts = [v for v in buf.cpu().tolist() if v]
