@@ -136,7 +136,7 @@ class Engine:
     #   "tc32" tensor cores with promoted accumulation (csrc/node_post_tc.cu; default of the tensor-core modes)
     #   "ffma" exact-fp32 CUDA-core kernel            "tc" tensor cores, plain TMEM accumulation
     # The tensor core accumulates in fp32 with truncation (measured bias -7e-7 relative at K = 128, growing linearly
-    # with K), which the h_V path amplifies: against the CPU oracle on fresh inputs (tools/diag_accuracy.py) the max
+    # with K), which the h_V path amplifies: against the CPU oracle on fresh inputs (tests/diag_accuracy.py) the max
     # chi error after 2 / 30 steps is 1.2e-4 / 3.0e-5 rad with "tc" (gate: 1e-4 at every step), 4.7e-5 / 9.2e-6 with
     # "ffma" and 4.5e-5 / 8.3e-6 with "tc32" (fp32 mode: 5.1e-5 / 6.7e-6); throughput 5.93 / 5.30 / 5.81 M.  The
     # residue prologue (points, A_i, N_j) is accuracy-neutral and always runs on the tensor cores in these modes.

@@ -169,7 +169,7 @@ def test_node_post_tc32_matches_cuda_core_kernel(case):
 def test_node_epilogue_options(node_epilogue):
     """The three homes of the per-residue node update: promoted tensor-core accumulation (default), plain TMEM
     accumulation (MODE 2 of edge_tc_kernel) and the CUDA-core kernel, all within the activation gate of one network
-    evaluation; only "tc" misses the 1e-4 rad gate after the first ODE steps (tools/diag_accuracy.py)."""
+    evaluation; only "tc" misses the 1e-4 rad gate after the first ODE steps (tests/diag_accuracy.py)."""
     from packppi_b200 import TDiffusionModule, weights
     dev = torch.device("cuda:0")
     g, b = load_golden("t1124")
