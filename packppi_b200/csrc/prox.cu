@@ -8,7 +8,8 @@
 //   atom14_kernel       one thread per residue, rigid frames in registers; also emits the chi rotation axes
 //   clash_nbr_*         residue neighbour list from the static backbone: CA distance < reach_i + reach_j + cutoff,
 //                       reach = rigorous bound on |CA - atom| over all chi  (built once per complex)
-//   clash_pair_kernel   16 lanes per residue (one per atom slot) walk the neighbour residues; a bounding-sphere test
+//   clash_pair_kernel   one warp per residue: two half-warps of 16 lanes (one lane per atom slot) walk the even and
+//                       the odd entries of the neighbour list and add their sums at the end; a bounding-sphere test
 //                       on the CURRENT atoms rejects most of them; every surviving 14x14 block is evaluated from
 //                       both sides, so each atom owns its loss and force: no atomics, fixed summation order.
 //                       Forces are projected on the chi axes (dL/dchi_k = sum_a (u_k x (p_a - o_k)) . F_a) in the
@@ -225,7 +226,8 @@ clash_pair_kernel(const float4* __restrict__ atoms, const float* __restrict__ bo
                   float w_uniform, float tol, float max_cut, int G, int S, float* __restrict__ per_res /*[R]*/,
                   float* __restrict__ grad_chi /*[R][4]*/, AdamArgs ad, float* __restrict__ partial /*[gridDim][2]*/) {
   const int lane16 = threadIdx.x & 15;
-  const int r = blockIdx.x * 8 + (threadIdx.x >> 4);
+  const int half = (threadIdx.x >> 4) & 1;  // which entries of the neighbour list this half-warp takes
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int R = S * G;
   const bool live = r < R;
   const int rr = live ? r : R - 1;
@@ -248,7 +250,7 @@ clash_pair_kernel(const float4* __restrict__ atoms, const float* __restrict__ bo
 
   // ---- between residues (clash.py:102-254)
   long long n0 = nbr_start[g], n1 = nbr_start[g + 1];
-  for (long long n = n0; n < n1; ++n) {
+  for (long long n = n0 + half; n < n1; n += 2) {
     int gj = nbr_list[n];
     int rj = s * G + gj;
     float dx = X[(size_t)gj * 42 + 3] - cax, dy = X[(size_t)gj * 42 + 4] - cay, dz = X[(size_t)gj * 42 + 5] - caz;
@@ -279,6 +281,12 @@ clash_pair_kernel(const float4* __restrict__ atoms, const float* __restrict__ bo
       }
     }
   }
+  // the two halves of the neighbour list (fixed order: even entries + odd entries); both half-warps continue with
+  // the totals
+  loss += __shfl_xor_sync(0xffffffffu, loss, 16);
+  fx += __shfl_xor_sync(0xffffffffu, fx, 16);
+  fy += __shfl_xor_sync(0xffffffffu, fy, 16);
+  fz += __shfl_xor_sync(0xffffffffu, fz, 16);
   // ---- within the residue (clash.py:7-99): every ordered pair adds its error to both atoms
   {
     int type = min(max((int)residue_type[g], 0), 20);
@@ -314,7 +322,7 @@ clash_pair_kernel(const float4* __restrict__ atoms, const float* __restrict__ bo
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
   const float pr = lsum * inv_i;
-  if (live && lane16 == 0 && per_res) per_res[r] = pr;
+  if (live && lane16 == 0 && half == 0 && per_res) per_res[r] = pr;
 
   float gk[4] = {0.f, 0.f, 0.f, 0.f};
   if (MODE != 0) {
@@ -333,14 +341,14 @@ clash_pair_kernel(const float4* __restrict__ atoms, const float* __restrict__ bo
       for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
       gk[k] = t;
     }
-    if (MODE == 1 && live && lane16 < 4) grad_chi[(size_t)r * 4 + lane16] = gk[lane16];
+    if (MODE == 1 && live && lane16 < 4 && half == 0) grad_chi[(size_t)r * 4 + lane16] = gk[lane16];
   }
 
   float sc_term = 0.f;
   if (MODE == 2) {
     // f(x) = mean_res |x' - z|^2 + lamda * mean_res clash(x'),  x' = where(mask, x, SC_D)   (optimize.py:33-45)
     const bool mine = ad.owned == nullptr || ad.owned[rr] != 0;
-    if (live && lane16 < 4) {
+    if (live && lane16 < 4 && half == 0) {
       size_t o = (size_t)r * 4 + lane16;
       bool mk = ad.mask[o] != 0 && mine;
       float x = ad.x[o], z = ad.z[o], s0 = ad.sc_d[o];
@@ -364,15 +372,15 @@ clash_pair_kernel(const float4* __restrict__ atoms, const float* __restrict__ bo
   const bool counted = (MODE != 2 || ad.owned == nullptr) ? true : (ad.owned[rr] != 0);
   if (partial) {
     // block partial sums (fixed order): [0] sum of per-residue clash, [1] sum of |x' - z|^2
-    __shared__ float red[2][8];
-    if (lane16 == 0) {
-      red[0][threadIdx.x >> 4] = (live && counted) ? pr : 0.f;
-      red[1][threadIdx.x >> 4] = (live && counted) ? sc_term : 0.f;
+    __shared__ float red[2][4];
+    if (lane16 == 0 && half == 0) {
+      red[0][threadIdx.x >> 5] = (live && counted) ? pr : 0.f;
+      red[1][threadIdx.x >> 5] = (live && counted) ? sc_term : 0.f;
     }
     __syncthreads();
     if (threadIdx.x < 2) {
       float t = 0.f;
-      for (int i = 0; i < 8; ++i) t += red[threadIdx.x][i];
+      for (int i = 0; i < 4; ++i) t += red[threadIdx.x][i];
       partial[(size_t)blockIdx.x * 2 + threadIdx.x] = t;
     }
   }
@@ -471,7 +479,7 @@ extern "C" int pp_clash_fwd_bwd(const float* tables, const float* lower, const f
                                                                 nullptr, (int)G, (int)S, nullptr, atom_exists,
                                                                 (float4*)atoms4, axes, bound);
   AdamArgs ad{};
-  unsigned blocks = (unsigned)((R + 7) / 8);
+  unsigned blocks = (unsigned)((R + 3) / 4);
   if (mode == 0)
     clash_pair_kernel<0><<<blocks, 128, 0, stream>>>((const float4*)atoms4, bound, axes, X, (const long long*)residue_type,
                                                      atom_exists, (const long long*)nbr_start, nbr_list, lower, upper,
@@ -486,7 +494,7 @@ extern "C" int pp_clash_fwd_bwd(const float* tables, const float* lower, const f
 }
 
 // Number of floats the proximal partial-sum workspace needs for R residue rows.
-extern "C" int64_t pp_prox_partial_floats(int64_t R) { return 2 * ((R + 7) / 8) + 8; }
+extern "C" int64_t pp_prox_partial_floats(int64_t R) { return 2 * ((R + 3) / 4) + 8; }
 
 // Clash mask and optimiser state from the starting angles (optimize.py:5-31,47-51): one loss evaluation,
 // its mean, mask = per_res > mean, z = SC_D*mask, x = z, Adam moments zero.  mean_out[0:2] = {unused, mean}.
@@ -502,7 +510,7 @@ extern "C" int pp_prox_init(const float* tables, const float* lower, const float
                                                                 nullptr, (int)G, 1, nullptr, atom_exists, (float4*)atoms4,
                                                                 axes, bound);
   AdamArgs ad{};
-  unsigned blocks = (unsigned)((G + 7) / 8);
+  unsigned blocks = (unsigned)((G + 3) / 4);
   clash_pair_kernel<0><<<blocks, 128, 0, stream>>>((const float4*)atoms4, bound, axes, X, (const long long*)residue_type,
                                                    atom_exists, (const long long*)nbr_start, nbr_list, lower, upper, tables,
                                                    nullptr, 0.f, tol, max_cut, (int)G, 1, per_res, nullptr, ad, partial);
@@ -540,7 +548,7 @@ extern "C" int pp_prox_step(const float* tables, const float* lower, const float
                                                                 bound);
   const float inv_n = 1.f / (float)(n_total > 0 ? n_total : G);  // mean over the residues of the WHOLE complex
   AdamArgs ad{x, m, v, z, sc_d, mask, snapshot, owned, step_size, bc2_sqrt, beta1, beta2, eps, inv_n};
-  unsigned blocks = (unsigned)((G + 7) / 8);
+  unsigned blocks = (unsigned)((G + 3) / 4);
   clash_pair_kernel<2><<<blocks, 128, 0, stream>>>((const float4*)atoms4, bound, axes, X, (const long long*)residue_type,
                                                    atom_exists, (const long long*)nbr_start, nbr_list, lower, upper, tables,
                                                    nullptr, lamda * inv_n, tol, max_cut, (int)G, 1, per_res, nullptr, ad,
