@@ -2,21 +2,28 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl packppi_b200|reference] [--complexes C]
 
-Workload (BASELINE.json configs[4]): a sweep of C = 64 synthetic two-chain complexes with
-L ~ U{200..800} residues (seed 64), 8 diffusion samples each, random-init weights (seed 0).  One bench "step" = one
-full pass over the sweep: for every complex the kNN graph, the edge embedding and 30 reverse-ODE steps of all 8
-samples.  The sweep is processed in micro-batches of 8 complexes (sorted by length, padded to the longest of the
-micro-batch).  Metric: residue.denoise-steps/s = sum(valid residues) x 8 samples x 30 / seconds.
-With N > 1 every rank runs its own sweep (same lengths, different coordinates): weak scaling, no data-path
-collective; the only NCCL call is the all_gather of the sampled angles at the end of each step.
+Workload (BASELINE.json configs[4]): ONE fixed sweep of C = 64 synthetic two-chain complexes
+with L ~ U{200..800} residues (seed 64), 8 diffusion samples each, random-init weights (seed 0).  One bench "step" =
+one full pass over the sweep: for every complex the kNN graph, the edge embedding and 30 reverse-ODE steps of all 8
+samples.  Metric: residue.denoise-steps/s = sum(valid residues) x 8 samples x 30 / seconds.
+With N > 1 the SAME sweep is partitioned over the ranks (`packppi_b200.shard.partition`: longest-first bin packing on
+the residue counts; the 8 samples of a complex share graph and edge embedding and stay together): strong scaling, no
+data-path collective; one pre-allocated `all_gather_into_tensor` returns every rank's sampled angles at the end of
+each step (`"scaling": "strong"`).  The line also carries `weak_scaling` (every rank runs a whole sweep of its own, as
+round 1 measured it) so that both curves can be read from the same run.  Each rank processes its complexes in
+micro-batches of 8 (sorted by length, padded to the longest of the micro-batch).
 
 `value`  : inputs resident in HBM, device-timed (CUDA events), max over ranks.
 `e2e`    : same pass through the public API (TDiffusionModule.sampling) from pinned HOST batches, including the
            host->device copy of every micro-batch and the device->host copy of the sampled angles.
-`roofline`: dominant kernel (edge_edge_kernel, the per-edge message MLP + FFN), timed with CUDA events around each
-           of its launches in one instrumented pass.
-`cpu_baseline` / `--impl reference`: the CPU oracle port (oracle/msc_oracle.py, dense like the reference, graph
-           rebuilt every step like the reference) on a bounded sample of the same sweep, all host threads.
+`roofline`: dominant kernel (the per-edge edge update), timed with CUDA events around each of its launches in one
+           instrumented pass; `roofline_clash`: the batched clash loss + gradient kernel on the same sweep's 512 items.
+`cpu_baseline` / `--impl reference`: the UNMODIFIED reference (`TDiffusionModule.sampling`,
+           /root/reference/src/models/TorsionalDiffusion.py:254-298, copied to baseline/_ref/ by
+           tools/install_reference.sh and imported under tools/ref_shims.py) on the box's host cores, all threads, on a
+           bounded, length-stratified sample of the same sweep (kind "reference"); the CPU oracle port is the fallback
+           only if baseline/_ref/ is absent (kind "port").
+`parity_check`: the GPU path against that reference run on one complex of the sample, reference noise injected.
 """
 import argparse
 import json
@@ -37,6 +44,9 @@ if ROOT not in sys.path:
 N_SAMPLES = 8
 N_ODE = 30
 MICRO = 8
+# arithmetic of the message-passing GEMMs per execution mode (the `dtype` key of the line)
+DTYPE = {"f16x3": "f32 via 3x split-f16 tensor-core products (fp32 accumulate, fp32-grade)", "fp32": "f32",
+         "f16": "f16 inputs, f32 accumulate"}
 # executed FLOPs of one edge_edge_kernel launch per residue row (K = 32 edges): first Linear 168 wide (h_E + pair
 # geometry; the h_V parts are hoisted per residue), two 128x128 Linears, FFN 128-512-128   
 EDGE_KERNEL_FLOP_PER_RES = 32 * 2 * (168 * 128 + 128 * 128 + 128 * 128 + 2 * 128 * 512)
@@ -122,62 +132,146 @@ class ClockSampler:
                 "power_w": statistics.median(pw) if pw else None, "power_limit_w": plim}
 
 
-def build_sweep(n_complexes, seed_base, rank):
+def sweep_items(n_complexes, seed_base=10_000):
+    """The fixed sweep: list of single-complex host batches (identical on every rank)."""
     from packppi_b200 import synthetic
-    from packppi_b200.batch import collate
     lengths = synthetic.sweep_lengths(n_complexes, 200, 800, seed=64)
-    items = [synthetic.make_complex(ch, seed=seed_base + 1000 * rank + i) for i, ch in enumerate(lengths)]
-    items.sort(key=lambda b: b.max_size)
+    return [synthetic.make_complex(ch, seed=seed_base + i) for i, ch in enumerate(lengths)]
+
+
+def micro_batches(items):
+    from packppi_b200.batch import collate
+    items = sorted(items, key=lambda b: b.max_size)
     micro = [collate(items[i:i + MICRO]) for i in range(0, len(items), MICRO)]
     residues = sum(int(b.residue_mask.sum()) for b in micro)
     return micro, residues
 
 
+def cpu_model_name():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
-def oracle_rate(batch, n_ode, threads):
-    """residue.steps/s of the CPU oracle (dense, graph rebuilt every step like the reference) on one complex."""
-    from oracle import msc_oracle as mo
-    from packppi_b200 import weights
-    torch.set_num_threads(threads)
-    sd = weights.make_state_dict(0)
-    g = torch.Generator().manual_seed(1)
-    x0 = ((torch.rand(batch.SC_D.shape, generator=g) * 2 - 1) * math.pi) * batch.SC_D_mask
-    t0 = time.perf_counter()
-    mo.sampling(sd, batch, x0, n_steps=n_ode, hoist=False)
-    dt = time.perf_counter() - t0
-    return float(batch.residue_mask.sum()) * n_ode / dt, dt
+def stratified(items, n):
+    """n complexes spread evenly over the length-sorted sweep (mid-points of n equal quantile bins)."""
+    order = sorted(range(len(items)), key=lambda i: (items[i].max_size, i))
+    n = max(1, min(n, len(order)))
+    return [items[order[min(len(order) - 1, (2 * k + 1) * len(order) // (2 * n))]] for k in range(n)]
+
+
+class ReferenceCPU:
+    """The unmodified reference on the host cores: `TDiffusionModule.sampling(batch)` exactly as
+    src/eval_diffusion.py:62 calls it (fp32, autograd graph and per-step graph rebuild included), with the bench
+    weights loaded through its own `load_state_dict`.  None of packppi_b200's kernels are on this path."""
+
+    def __init__(self, threads):
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import ref_shims
+        from packppi_b200 import weights
+        if not ref_shims.available():
+            raise FileNotFoundError("baseline/_ref is absent: run tools/install_reference.sh in the build container")
+        torch.set_num_threads(threads)
+        self.threads = threads
+        self.ref = ref_shims.import_reference()
+        self.model = ref_shims.build_reference_model(self.ref)
+        self.model.load_state_dict(weights.make_state_dict(0))
+        self.kind = "reference"
+        self.drawn = None
+        orig = self.model.add_sc_noise
+
+        def recording(batch, t):  # keeps the reference's own initial noise draw for the parity check
+            out = orig(batch, t)
+            self.drawn = out[0].detach().clone()
+            return out
+
+        self.model.add_sc_noise = recording
+
+    def sample(self, b, seed=1):
+        """-> (sampled angles [1,L,4], seconds)"""
+        d = self.ref.Data(**{k: (v.clone() if torch.is_tensor(v) else v) for k, v in b.items()})
+        torch.manual_seed(seed)
+        t0 = time.perf_counter()
+        out = self.model.sampling(d, use_proximal=False)
+        return out.detach(), time.perf_counter() - t0
+
+
+class OraclePortCPU:
+    """Fallback when baseline/_ref is absent: the CPU oracle port (dense like the reference, graph rebuilt every step)."""
+
+    def __init__(self, threads):
+        from packppi_b200 import weights
+        torch.set_num_threads(threads)
+        self.threads, self.kind, self.drawn = threads, "port", None
+        self.sd = weights.make_state_dict(0)
+
+    def sample(self, b, seed=1):
+        from oracle import msc_oracle as mo
+        g = torch.Generator().manual_seed(seed)
+        x0 = ((torch.rand(b.SC_D.shape, generator=g) * 2 - 1) * math.pi) * b.SC_D_mask
+        self.drawn = x0
+        t0 = time.perf_counter()
+        out = mo.sampling(self.sd, b, x0, n_steps=N_ODE, hoist=False)
+        return out, time.perf_counter() - t0
+
+
+def cpu_arm(threads):
+    try:
+        return ReferenceCPU(threads)
+    except (FileNotFoundError, ImportError) as e:
+        print(f"[bench] reference unavailable ({e}); timing the oracle port instead", file=sys.stderr)
+        return OraclePortCPU(threads)
 
 
 def run_reference(args):
-    """`--impl reference`: the reference algorithm on the host cores (oracle port; the reference itself is Python on
-    torch and cannot travel to the GPU box).  Bounded sample: one ~300-residue complex of the sweep,
-    n_ode reverse-ODE steps per bench step, calibrated so that the whole run ends within a few minutes."""
+    """`--impl reference`: every bench step = one call of the reference's `sampling` (30 reverse-ODE steps, 1 diffusion
+    sample) on ONE complex of the sweep; the K timed steps walk K complexes spread evenly over the length-sorted sweep,
+    so the rate is that of a length-stratified sample of the workload.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from packppi_b200 import synthetic
     threads = os.cpu_count() or 1
-    lengths = synthetic.sweep_lengths(args.complexes, 200, 800, seed=64)
-    ch = min(lengths, key=lambda c: abs(sum(c) - 300))
-    b = synthetic.make_complex(ch, seed=7)
-    L = sum(ch)
-    _, dt1 = oracle_rate(b, 1, threads)  # calibration (also warms the thread pool)
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    n_ode = int(max(1, min(N_ODE, budget / max(dt1, 1e-3))))
-    for _ in range(args.warmup):
-        oracle_rate(b, n_ode, threads)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        oracle_rate(b, n_ode, threads)
-    dt = time.perf_counter() - t0
-    value = L * n_ode * args.steps / dt
-    sample = f"1 complex of {L} residues (sweep member), 1 sample, {n_ode} reverse-ODE steps per bench step"
+    items = sweep_items(args.complexes)
+    arm = cpu_arm(threads)
+    timed = stratified(items, args.steps)
+    timed = [timed[k % len(timed)] for k in range(args.steps)]
+    # bound the run: ~1.5 s per 10 k residue.steps on 16 cores; shrink to the shorter half of the sweep if K is large
+    _, dt0 = arm.sample(min(items, key=lambda b: b.max_size))
+    rate0 = min(items, key=lambda b: b.max_size).max_size * N_ODE / dt0
+    est = sum(b.max_size for b in timed) * N_ODE / rate0
+    bounded = ""
+    if est > 240.0:
+        keep = sorted(items, key=lambda b: b.max_size)[:max(1, int(len(items) * 240.0 / est))]
+        timed = stratified(keep, args.steps)
+        timed = [timed[k % len(timed)] for k in range(args.steps)]
+        bounded = f" (restricted to the {len(keep)} shortest complexes to bound the run)"
+    warm = stratified(items, max(1, args.warmup))[:1] * max(0, args.warmup - 1)  # the calibration call was warm-up 1
+    for b in warm:
+        arm.sample(b)
+    res, secs = 0, 0.0
+    for b in timed:
+        _, dt = arm.sample(b)
+        res += int(b.residue_mask.sum())
+        secs += dt
+    value = res * N_ODE / secs
+    sample = (f"{args.steps} calls of TDiffusionModule.sampling (30 reverse-ODE steps, 1 diffusion sample), one "
+              f"complex of the sweep per bench step, {min(b.max_size for b in timed)}-{max(b.max_size for b in timed)} "
+              f"residues spread evenly over the length-sorted sweep{bounded}; {res} residues, {secs:.1f} s; "
+              f"CPU: {cpu_model_name()}")
+    cfg = workload_config(args)
+    cfg["reference_sample"] = sample
     line = {"impl": "reference", "metric": "residue.denoise-steps/s", "value": value, "unit": "residue.steps/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args),
-            "cpu_baseline": {"value": value, "unit": "residue.steps/s", "cores": threads, "kind": "port",
-                             "sample": sample},
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfg,
+            "cpu_baseline": {"value": value, "unit": "residue.steps/s", "cores": threads, "kind": arm.kind,
+                             "sample": sample, "cpu_model": cpu_model_name()},
             "e2e": {"value": value, "unit": "residue.steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -285,13 +379,14 @@ def main():
     ap.add_argument("--complexes", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the clash-grad @5k and single-complex timings")
+    ap.add_argument("--no-weak", action="store_true", help="skip the extra weak-scaling pass at N > 1")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
     import torch.distributed as dist
 
-    from packppi_b200 import TDiffusionModule, _lib, weights
+    from packppi_b200 import TDiffusionModule, _lib, shard, weights
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -304,49 +399,61 @@ def main():
     model = TDiffusionModule()
     model.load_state_dict(weights.make_state_dict(0))
     model = model.to(dev).eval()
-    micro_host, residues = build_sweep(args.complexes, 10_000, rank)
-    micro_pinned = [b.pin_memory() for b in micro_host]
-    micro_dev = [b.to(dev) for b in micro_host]
-    units = residues * N_SAMPLES * N_ODE
+    items = sweep_items(args.complexes)                      # the fixed sweep, identical on every rank
+    lengths = [int(b.max_size) for b in items]
+    plan = shard.partition(lengths, world)                   # strong scaling: this rank's share of the sweep
+    total_residues = sum(int(b.residue_mask.sum()) for b in items)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    gather_buf = None
 
-    host_out = [torch.empty(N_SAMPLES, b.X.shape[0], b.X.shape[1], 4, dtype=torch.float32).pin_memory()
-                for b in micro_host]
+    class Pass:
+        """Device / pinned-host copies of a list of complexes as micro-batches + pre-allocated output buffers."""
 
-    def one_pass(batches, from_host):
-        """One pass over the sweep.  from_host: every micro-batch is copied from pinned host memory and its sampled
-        angles are copied back to pinned host memory (both asynchronous on the compute stream; the caller's
-        synchronize at the end of the timed region waits for the last byte)."""
-        outs = []
-        for i, b in enumerate(batches):
-            bd = b.to(dev, non_blocking=True) if from_host else b
-            model._graph_cache = (None, model._graph_cache[1])  # new complex: graph + edge embedding are rebuilt every call
-            chi = model.sampling(bd, n_samples=N_SAMPLES, generator=gen)
-            if from_host:
-                host_out[i].copy_(chi, non_blocking=True)
-                outs.append(host_out[i])
-            else:
-                outs.append(chi)
-        return outs
+        def __init__(self, its, gather_cap=None):
+            self.micro_host, self.residues = micro_batches(its) if its else ([], 0)
+            self.pinned = [b.pin_memory() for b in self.micro_host]
+            self.dev = [b.to(dev) for b in self.micro_host]
+            self.host_out = [torch.empty(N_SAMPLES, b.X.shape[0], b.X.shape[1], 4, dtype=torch.float32).pin_memory()
+                             for b in self.micro_host]
+            self.sizes = [N_SAMPLES * b.X.shape[0] * b.X.shape[1] * 4 for b in self.micro_host]
+            self.flat = self.all = None
+            if gather_cap is not None:  # pre-allocated all_gather buffers: [cap] per rank -> [world, cap]
+                self.flat = torch.zeros(gather_cap, dtype=torch.float32, device=dev)
+                self.all = torch.empty(world, gather_cap, dtype=torch.float32, device=dev)
 
-    def gather(outs):
-        if world == 1:
-            return
-        flat = torch.cat([o.reshape(-1) for o in outs])
-        bufs = [torch.empty_like(flat) for _ in range(world)]
-        dist.all_gather(bufs, flat)
+        def run(self, from_host, gather):
+            """One pass.  from_host: every micro-batch is copied from pinned host memory and its sampled angles are
+            copied back to pinned host memory (asynchronous on the compute stream; the synchronize that ends the timed
+            region waits for the last byte)."""
+            o = 0
+            src = self.pinned if from_host else self.dev
+            for i, b in enumerate(src):
+                bd = b.to(dev, non_blocking=True) if from_host else b
+                model._graph_cache = (None, model._graph_cache[1])  # new complexes: graph + edge embedding rebuilt
+                chi = model.sampling(bd, n_samples=N_SAMPLES, generator=gen)
+                if from_host:
+                    self.host_out[i].copy_(chi, non_blocking=True)
+                if gather and self.flat is not None:
+                    self.flat[o:o + self.sizes[i]].copy_(chi.reshape(-1))
+                    o += self.sizes[i]
+            if gather and self.flat is not None and world > 1:
+                dist.all_gather_into_tensor(self.all, self.flat)
 
-    def timed(batches, from_host, steps):
+    def padded_floats(its):
+        mb, _ = micro_batches(its) if its else ([], 0)
+        return sum(N_SAMPLES * b.X.shape[0] * b.X.shape[1] * 4 for b in mb)
+
+    cap = max(padded_floats([items[i] for i in plan[r]]) for r in range(world))
+    mine = Pass([items[i] for i in plan[rank]], gather_cap=cap)
+    units = total_residues * N_SAMPLES * N_ODE               # whole job, all ranks together
+
+    def timed(ps, from_host, steps, gather=True):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            outs = one_pass(batches, from_host)
-            if not from_host:
-                gather(outs)
+            ps.run(from_host, gather)
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -359,47 +466,61 @@ def main():
     if rank == 0:
         clocks.start()
     for _ in range(args.warmup):
-        one_pass(micro_dev, False)
+        mine.run(False, True)
     if rank == 0:
         clocks.wait_first_sample()
     _lib.LAUNCHES = 0
     t_a = time.monotonic()
-    ms = timed(micro_dev, False, args.steps)
+    ms = timed(mine, False, args.steps)
     t_b = time.monotonic()
     launches = _lib.LAUNCHES
     clk = clocks.window(t_a, t_b) if rank == 0 else None
-    value = world * units * args.steps / (ms / 1e3)
+    value = units * args.steps / (ms / 1e3)
 
-    one_pass(micro_pinned, True)  # warm-up of the host path: its allocations differ from the device-resident pass
+    mine.run(True, True)  # warm-up of the host path: its allocations differ from the device-resident pass
     t_a = time.monotonic()
-    if os.environ.get("PP_BENCH_DEBUG"):
-        for i in range(4):
-            print(f"[debug] e2e pass {i}: {timed(micro_pinned, True, 1):.1f} ms; device pass: "
-                  f"{timed(micro_dev, False, 1):.1f} ms", file=sys.stderr, flush=True)
-    ms_e2e = timed(micro_pinned, True, max(1, min(args.steps, 2)))
-    clk_e2e = clocks.window(t_a, time.monotonic()) if rank == 0 else None
-    clocks.stop()
     e2e_steps = max(1, min(args.steps, 2))
-    e2e_value = world * units * e2e_steps / (ms_e2e / 1e3)
-    h2d = sum(b.nbytes() for b in micro_host)
-    d2h = sum(int(b.X.shape[0] * b.X.shape[1]) for b in micro_host) * N_SAMPLES * 4 * 4
+    ms_e2e = timed(mine, True, e2e_steps)
+    clk_e2e = clocks.window(t_a, time.monotonic()) if rank == 0 else None
+    e2e_value = units * e2e_steps / (ms_e2e / 1e3)
+    h2d = torch.tensor([float(sum(b.nbytes() for b in mine.micro_host)),
+                        float(sum(int(b.X.shape[0] * b.X.shape[1]) for b in mine.micro_host) * N_SAMPLES * 4 * 4)],
+                       device=dev)
+    if world > 1:
+        dist.all_reduce(h2d)  # bytes of the whole job
+    h2d, d2h = int(h2d[0].item()), int(h2d[1].item())
+
+    # weak-scaling curve (round 1's definition): every rank runs a WHOLE sweep of its own, no gather
+    weak = None
+    if world > 1 and not args.no_weak:
+        from packppi_b200 import synthetic
+        wl = synthetic.sweep_lengths(args.complexes, 200, 800, seed=64)
+        whole = Pass([synthetic.make_complex(ch, seed=10_000 + 1000 * rank + i) for i, ch in enumerate(wl)])
+        whole.run(False, False)
+        wsteps = max(1, min(args.steps, 3))
+        wms = timed(whole, False, wsteps, gather=False)
+        weak = {"value": world * whole.residues * N_SAMPLES * N_ODE * wsteps / (wms / 1e3), "unit": "residue.steps/s",
+                "ms_per_step": wms / wsteps, "steps": wsteps,
+                "note": "one whole sweep per rank (same lengths, different coordinates), no gather"}
+        del whole
+    clocks.stop()
 
     # instrumented pass: CUDA events around every launch of the dominant kernel (the per-edge edge update)
     mode, cluster = model.engine(dev).mode, model.kernel_cluster
     pkey = "pp_ipmp_edge_edge" if mode == "fp32" else "pp_ipmp_edge_tc:edge"
     _lib.PROFILE = {pkey: []}
-    t_pass = timed(micro_dev, False, 1)
+    t_pass = timed(mine, False, 1)
     ev = _lib.PROFILE[pkey]
     _lib.PROFILE = None
     torch.cuda.synchronize()
     k_ms = [a.elapsed_time(b) for a, b, _ in ev]
     # algorithmic work = the valid residues (padding rows of a ragged micro-batch are not work; the tensor-core
     # kernels skip them).  Every micro-batch launches the kernel for 2 layers x 30 steps.
-    valid = sum(int(b.residue_mask.sum()) for b in micro_host) * N_SAMPLES
+    valid = mine.residues * N_SAMPLES
     peaks = measured_peaks()
     if k_ms:
         tot_ms, tot_rows = sum(k_ms), valid * 2 * N_ODE
-        assert len(k_ms) == len(micro_host) * 2 * N_ODE
+        assert len(k_ms) == len(mine.micro_host) * 2 * N_ODE
         tflops = EDGE_KERNEL_FLOP_PER_RES * tot_rows / (tot_ms * 1e-3) / 1e12
         gbs = EDGE_KERNEL_BYTES_PER_RES * tot_rows / (tot_ms * 1e-3) / 1e9
         kname = {"fp32": "edge_edge_kernel (per-edge message MLP + FFN, fp32 FFMA on CUDA cores)",
@@ -421,33 +542,55 @@ def main():
     else:
         roof = None
 
+    roof_clash = run_batched_clash(items, dev, peaks) if rank == 0 and not args.no_secondary else None
+
     secondary = None
     if rank == 0 and not args.no_secondary:
         secondary = run_secondary(model, dev, not args.no_cpu_baseline)
+    if not args.no_secondary:
+        slab = run_slab_proximal(dev, world, rank)  # collective: every rank takes part
+        if secondary is not None:
+            secondary.update(slab)
 
-    cpu = None
+    cpu = parity = None
     if rank == 0 and not args.no_cpu_baseline:
-        small = min(micro_host[0:1], key=lambda b: b.max_size)
-        from packppi_b200.batch import ComplexBatch
-        one = ComplexBatch(**{k: (v[:1] if torch.is_tensor(v) else v) for k, v in small.items()})
-        Lc = int(one.residue_mask.sum())
-        for k, v in list(one.items()):  # strip the padding of the micro-batch
-            if torch.is_tensor(v):
-                one[k] = v[:, :Lc].contiguous()
-        one["num_proteins"], one["max_size"] = 1, Lc
-        threads = os.cpu_count() or 1
-        rate, dt = oracle_rate(one, 10, threads)
-        cpu = {"value": rate, "unit": "residue.steps/s", "cores": threads, "kind": "port",
-               "sample": f"1 complex of {Lc} residues (shortest of the sweep), 1 sample, 10 reverse-ODE steps, {dt:.1f} s"}
+        arm = cpu_arm(os.cpu_count() or 1)
+        picks = stratified(items, 4)
+        res, secs, check = 0, 0.0, None
+        for j, b in enumerate(picks):
+            out, dt = arm.sample(b)
+            res += int(b.residue_mask.sum())
+            secs += dt
+            if j == 1:  # parity check on the second pick (~350 residues), the reference's own noise injected
+                got = model.sampling(b.to(dev), init_SC_D=arm.drawn.to(dev)).cpu()
+                d = (got - out).abs()
+                d = torch.minimum(d, 2 * math.pi - d)
+                check = {"against": arm.kind, "residues": int(b.max_size), "denoise_steps": N_ODE,
+                         "max_chi_diff_rad": float(d.max()), "mean_chi_diff_rad": float(d.mean()),
+                         "tolerance_rad": 1e-4, "pass": bool(d.max() < 1e-4)}
+        parity = check
+        cpu = {"value": res * N_ODE / secs, "unit": "residue.steps/s", "cores": arm.threads, "kind": arm.kind,
+               "cpu_model": cpu_model_name(),
+               "sample": f"{len(picks)} complexes of the sweep at the 1/8, 3/8, 5/8, 7/8 length quantiles "
+                         f"({', '.join(str(int(b.max_size)) for b in picks)} residues), 1 diffusion sample, full 30 "
+                         f"reverse-ODE steps each through TDiffusionModule.sampling, {secs:.1f} s"}
 
     if rank == 0:
+        cfg = workload_config(args)
+        cfg["parallelism"] = (f"the fixed sweep partitioned over {world} rank(s) by residue count "
+                              "(packppi_b200.shard.partition), no data-path collective, one all_gather_into_tensor of "
+                              "the sampled angles per step")
         line = {"metric": "residue.denoise-steps/s", "value": value, "unit": "residue.steps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(args), "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
+                "scaling": "strong", "vs_baseline": None, "dtype": DTYPE.get(mode, mode), "data": "synthetic",
+                "config": cfg, "roofline": roof, "roofline_clash": roof_clash, "cpu_baseline": cpu,
+                "parity_check": parity, "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": "residue.steps/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / e2e_steps, "clocks": clk_e2e},
-                "gpu_launches": launches, "residues_per_gpu": residues, "secondary": secondary}
+                "gpu_launches": launches, "launches_note": "kernels launched by rank 0 inside the timed region",
+                "residues_total": total_residues, "residues_this_rank": mine.residues,
+                "rank_residue_share": [sum(lengths[i] for i in plan[r]) for r in range(world)],
+                "weak_scaling": weak, "secondary": secondary}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -9,7 +9,7 @@ Importing the package needs no GPU; calling a kernel without the built extension
 from .batch import ComplexBatch, collate  # noqa: F401
 from .featurize import protein_to_batch, proteins_to_batch_device  # noqa: F401
 from .components import (compute_residue_clash, find_clash_mask, get_atom14_coords,  # noqa: F401
-                         proximal_optimizer)
+                         host_staging, proximal_optimizer)
 from .model import MpnnNet, ProteinEncoder, TDiffusionModule  # noqa: F401
 
 __version__ = "0.1.0"

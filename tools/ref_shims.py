@@ -1,8 +1,9 @@
-"""Import the UNMODIFIED reference (/root/reference) in this container.
+"""Import the UNMODIFIED reference: /root/reference in the build container, or the copy that
+tools/install_reference.sh puts under baseline/_ref/ (git-ignored, shipped to the GPU box).
 
-Test infrastructure only: used by tools/gen_tables.py and tools/make_golden.py to
-produce committed numeric fixtures.  Nothing in packppi_b200/, bench.py, smoke() or
-the `-m gpu` tests imports this file; /root/reference does not exist on the GPU box.
+Test / baseline infrastructure only: used by tools/gen_tables.py and tools/make_golden.py to
+produce committed numeric fixtures, by bench.py's CPU legs (`--impl reference`, `cpu_baseline`) and by
+tests/test_dropin_reference.py.  Nothing in packppi_b200/ imports this file.
 
 The reference needs ten third-party modules that are absent here.
 They are only touched at import time or by code outside the sampling / proximal
@@ -13,7 +14,21 @@ import sys
 import types
 import inspect
 
-REFERENCE_ROOT = os.environ.get("PACKPPI_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_INSTALLED = os.path.normpath(os.path.join(_HERE, "..", "baseline", "_ref"))  # tools/install_reference.sh
+
+
+def _default_root():
+    if os.environ.get("PACKPPI_REFERENCE"):
+        return os.environ["PACKPPI_REFERENCE"]
+    return "/root/reference" if os.path.isdir("/root/reference/src") else _INSTALLED
+
+
+REFERENCE_ROOT = _default_root()
+
+
+def available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "src"))
 
 
 class AttrDict(dict):
@@ -102,7 +117,11 @@ def install():
     _module("torch_scatter", scatter_add=None)
     _module("freesasa")
     bio = _module("Bio")
-    biopdb = _module("Bio.PDB", PDBParser=_Anything, NeighborSearch=_Anything, Selection=_Anything)
+    if _HERE not in sys.path:
+        sys.path.insert(0, _HERE)
+    import mini_biopdb  # the few Bio.PDB classes the reference's file readers touch
+    biopdb = _module("Bio.PDB", PDBParser=mini_biopdb.PDBParser, NeighborSearch=mini_biopdb.NeighborSearch,
+                     Selection=mini_biopdb.Selection)
     bio.PDB = biopdb
     _module("pyrootutils", setup_root=lambda *a, **k: None)
 
