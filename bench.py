@@ -369,6 +369,107 @@ def run_secondary(model, dev, with_cpu):
     return out
 
 
+CLASH_BYTES_PER_RES = 330  # backbone 36 + chi 16 + type/index 8 in, atom records, 16 + 4 out
+
+
+def run_batched_clash(items, dev, peaks):
+    """`roofline_clash`: the clash loss + analytic gradient (atom14 rebuild included) and the full 50-step PackPPI-Prox
+    over the sweep's 512 (complex, sample) items, micro-batch by micro-batch (B = 8 complexes x S = 8 decoys per
+    launch) - the batched variant for which SURVEY §8d asks an HBM fraction (~330 B per residue and evaluation)."""
+    from packppi_b200 import _lib, proximal_optimizer
+    from packppi_b200.components import clash_context
+    micro, residues = micro_batches(items)
+    rows = residues * N_SAMPLES
+    gen = torch.Generator(device=dev).manual_seed(77)
+    work = []
+    for b in micro:
+        bd = b.to(dev)
+        chi = ((torch.rand(N_SAMPLES, *bd.SC_D.shape, device=dev, generator=gen) * 2 - 1) * math.pi) * bd.SC_D_mask
+        cc = clash_context(bd)
+        w = torch.ones(chi.numel() // 4, device=dev)
+        work.append((bd, chi.contiguous(), cc, w))
+    def evals():
+        for bd, chi, cc, w in work:
+            cc.evaluate(chi.reshape(-1, 4), res_w=w)
+
+    for _ in range(3):
+        evals()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        evals()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    gbs = CLASH_BYTES_PER_RES * rows / (ms * 1e-3) / 1e9
+    # the 50-step proximal loop on the same items (first call eager, second captures the CUDA graph, then replays)
+    t_prox = 0.0
+    accepted = 0
+    for bd, chi, cc, w in work:
+        run = lambda: cc.proximal(chi.reshape(-1, 4), 1.0, 50)  # noqa: E731
+        run(); run()
+        torch.cuda.synchronize()
+        e0.record()
+        _, losses, _ = run()
+        e1.record()
+        torch.cuda.synchronize()
+        t_prox += e0.elapsed_time(e1)
+        accepted += int((losses[-1] < losses[0]).sum())
+    n_items = len(items) * N_SAMPLES
+    return {"kernel": "atom14_kernel + clash_pair_kernel<1> (loss + analytic dL/dchi), batched over B x S items",
+            "bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+            "peak_source": f"{peaks['src']} HBM copy bandwidth", "traffic": None,
+            "algorithmic_bytes_per_launch": CLASH_BYTES_PER_RES * rows / len(work), "bytes_per_residue": CLASH_BYTES_PER_RES,
+            "avg_launch_ms": ms / len(work), "launches": len(work), "residue_rows": rows, "items": n_items,
+            "evaluations_per_s": n_items / (ms * 1e-3), "residue_evals_per_s": rows / (ms * 1e-3),
+            "note": "latency / L2 bound: the pair kernel walks neighbour lists with dependent loads; the HBM fraction is "
+                    "reported because SURVEY §8d asks for it on the batched variant, not because HBM binds",
+            "proximal_50_steps_all_items_ms": t_prox, "proximal_items_per_s": n_items / (t_prox * 1e-3),
+            "proximal_items_accepted": accepted}
+
+
+def run_slab_proximal(dev, world, rank):
+    """BASELINE configs[3]: PackPPI-Prox of ONE large complex cut into `world` spatial slabs (packppi_b200.shard.
+    SlabProximal; one NCCL all-gather of the owned angles per step, the loop replayed as one CUDA graph).  Collective:
+    every rank takes part; the numbers are the max over ranks."""
+    import torch.distributed as dist
+
+    from packppi_b200 import get_atom14_coords, shard, synthetic
+    out = {}
+    for tag, chains in (("5k", 10), ("50k", 100)):
+        b = synthetic.make_complex((500,) * chains, seed=5000 if chains == 10 else 50000).to(dev)
+        b["X"] = (get_atom14_coords(b.X, b.residue_type, b.BB_D, b.SC_D) * b.atom_mask[..., None]).contiguous()
+        t0 = time.perf_counter()
+        sp = shard.SlabProximal(b, 12.0, 0.5)
+        torch.cuda.synchronize()
+        setup_ms = 1e3 * (time.perf_counter() - t0)
+        sp.run(b.SC_D, 1.0, 50)
+        sp.run(b.SC_D, 1.0, 50)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        e0.record()
+        for _ in range(reps):
+            _, losses = sp.run(b.SC_D, 1.0, 50)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / reps, float(len(sp.local))], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        out[f"slab_proximal_50_steps_ms_{tag}"] = float(ms[0])
+        out[f"slab_proximal_local_residues_max_{tag}"] = int(ms[1])
+        out[f"slab_proximal_setup_ms_{tag}"] = setup_ms
+        out[f"slab_proximal_loss_first_last_{tag}"] = [float(losses[0]), float(losses[-1])]
+        del sp, b
+        torch.cuda.empty_cache()
+    out["slab_proximal_world"] = world
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -542,15 +643,12 @@ def main():
     else:
         roof = None
 
+    slab = run_slab_proximal(dev, world, rank) if not args.no_secondary else {}  # collective: every rank takes part
     roof_clash = run_batched_clash(items, dev, peaks) if rank == 0 and not args.no_secondary else None
-
     secondary = None
     if rank == 0 and not args.no_secondary:
         secondary = run_secondary(model, dev, not args.no_cpu_baseline)
-    if not args.no_secondary:
-        slab = run_slab_proximal(dev, world, rank)  # collective: every rank takes part
-        if secondary is not None:
-            secondary.update(slab)
+        secondary.update(slab)
 
     cpu = parity = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -593,6 +691,7 @@ def main():
                 "weak_scaling": weak, "secondary": secondary}
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()  # rank 0's CPU baseline runs last: the others wait here instead of tearing the group down
         dist.destroy_process_group()
 
 

@@ -98,7 +98,7 @@ int pp_ipmp_edge_edge(const float* weights, int64_t layer, const float* geo, con
 /* Tensor-core (tcgen05 / TMEM) version of pp_ipmp_edge_node (path 0) and pp_ipmp_edge_edge (path 1): same inputs,
  * same outputs.  wstream = operand images of this layer and path (pp_tc_stream_floats() floats, built by
  * packppi_b200.weights.pack_tc_stream: fp16 (hi, lo) image pairs, kind::f16 MMAs).  passes 3 = split fp16
- * (fp32-grade), 1 = plain fp16 inputs; cluster = 1, 2 or 4 CTAs that share (multicast) the weight stream.
+ * (fp32-grade), 1 = plain fp16 inputs; cluster = 1 or 2 CTAs that share (multicast) the weight stream.
  * msum [G] = mean of mask_attend over K (pp_knn_build): tiles whose residues all have msum == 0 (padding) are
  * skipped and their output rows left untouched (cluster == 1; zero the buffers once, the kernels of this library
  * never write anything else there).  out = accsum [S*G][128] or hE_out [S*G][K][128]; hE_in / hE_out
@@ -109,15 +109,10 @@ int pp_ipmp_edge_tc(const float* weights, int64_t layer, int64_t path, const flo
                     int64_t S, const float* hE_in, int64_t he_shared, const float* wsA, const float* wsN,
                     const float* wsP, float* out, int64_t passes, int64_t cluster, pp_stream_t stream);
 
-/* Tensor-core version of pp_ipmp_node_post (reference layers.py:127-132), same kernel family: tile = 128 residue
- * rows.  wstream = operand images of path 2 of this layer; hV [S*G][128] is updated in place. */
-int pp_ipmp_node_post_tc(const float* weights, int64_t layer, const float* wstream, const float* msum,
-                         const float* residue_mask, int64_t G, int64_t K, int64_t S, const float* wsAcc, float* hV,
-                         int64_t passes, int64_t cluster, pp_stream_t stream);
-
 /* pp_ipmp_node_post on the tensor cores with fp32-grade ("promoted") accumulation: every K = 16 step of a GEMM goes
  * into a fresh TMEM accumulator and the row threads sum the steps in fp32 registers, because the tensor core's own
- * fp32 accumulation truncates (csrc/node_post_tc.cu).  Same arguments as pp_ipmp_node_post_tc. */
+ * fp32 accumulation truncates (csrc/node_post_tc.cu).  wstream = operand images of path 2 of this layer; hV
+ * [S*G][128] is updated in place (reference layers.py:127-132). */
 int pp_ipmp_node_post_tc32(const float* weights, int64_t layer, const float* wstream, const float* msum,
                            const float* residue_mask, int64_t G, int64_t K, int64_t S, const float* wsAcc, float* hV,
                            pp_stream_t stream);
@@ -180,37 +175,41 @@ int pp_clash_fwd_bwd(const float* tables, const float* lower, const float* upper
                      int64_t mode, const float* res_w, float* per_res, float* grad_chi, float* atoms4, float* axes,
                      float* bound, pp_stream_t stream);
 
-/* proximal_optimizer (models/components/optimize.py:5-73), one complex (B = 1, S = 1).
- * pp_prox_init: find_clash_mask + optimiser state.  mean_out[1] = mean per-residue loss.
- * pp_prox_step: one Adam step; loss_out[0] = loss before the update (the value the reference appends to
- * loss_list), loss_out[1] = mean per-residue clash; snapshot = where(mask, x_new, SC_D).
+/* proximal_optimizer (models/components/optimize.py:5-73) for S samples of a padded batch of B complexes.  The
+ * reference handles one complex per call (optimize.py:27 asserts num_proteins == 1) and the notebooks loop over
+ * decoys; here the S*B (sample, complex) items are independent problems sharing every launch.  Rows: item
+ * it = s*B + b owns rows s*B*L + b*L + [0, n_res[b]); n_res int32 [B] (NULL: every complex has L residues) gives the
+ * unpadded residue counts, over which the reference's means are taken.
+ * pp_prox_init: find_clash_mask + optimiser state per item.  mean_out [S*B][2], slot 1 = mean per-residue loss.
+ * pp_prox_step: one Adam step of every item in two launches (atom14 rebuild, pair kernel).  The objective of a step
+ *   is left as per-row terms in loss_rows [S*B*L][2]; the NEXT call reduces them into prev_loss_out [S*B][2]
+ *   (NULL on the first step) in the tail blocks of its rebuild launch, and pp_prox_loss reduces the last step.
+ *   loss[it][0] = objective before the update (the value the reference appends to loss_list), loss[it][1] = mean
+ *   per-residue clash; snapshot = where(mask, x_new, SC_D).
  * step_size = lr / (1 - beta1^t), bc2_sqrt = sqrt(1 - beta2^t) as torch.optim.Adam computes them on the host. */
-int64_t pp_prox_partial_floats(int64_t R);
 int pp_prox_init(const float* tables, const float* lower, const float* upper, const float* X,
                  const int64_t* residue_type, const float* atom_exists, const int64_t* nbr_start,
-                 const int32_t* nbr_list, const float* sc_d, int64_t G, float tol, float max_cut, uint8_t* mask,
-                 float* z, float* x, float* m, float* v, float* per_res, float* mean_out, float* atoms4, float* axes,
-                 float* bound, float* partial, pp_stream_t stream);
+                 const int32_t* nbr_list, const float* sc_d, int64_t B, int64_t L, int64_t S, const int32_t* n_res,
+                 float tol, float max_cut, uint8_t* mask, float* z, float* x, float* m, float* v, float* per_res,
+                 float* mean_out, float* atoms4, float* axes, float* bound, float* loss_rows, pp_stream_t stream);
 int pp_prox_step(const float* tables, const float* lower, const float* upper, const float* X,
                  const int64_t* residue_type, const float* atom_exists, const int64_t* nbr_start,
                  const int32_t* nbr_list, const float* sc_d, const uint8_t* mask, const float* z, float* x, float* m,
-                 float* v, int64_t G, float tol, float max_cut, float lamda, float step_size, float bc2_sqrt,
-                 float beta1, float beta2, float eps, float* snapshot, float* loss_out, float* per_res, float* atoms4,
-                 float* axes, float* bound, float* partial, const uint8_t* owned, int64_t n_total, pp_stream_t stream);
-/* Slab-partitioned complex (one rank per slab): the arrays hold the rank's owned residues plus
- * the halo; owned uint8 [G] (NULL = all) marks the residues this rank optimises and counts in loss_out, n_total is the
- * residue count of the whole complex (0 = G).  pp_prox_init_from_mean builds mask / z / x from per_res and the
- * all-reduced mean[1]. */
+                 float* v, int64_t B, int64_t L, int64_t S, const int32_t* n_res, float tol, float max_cut, float lamda,
+                 float step_size, float bc2_sqrt, float beta1, float beta2, float eps, float* snapshot,
+                 float* prev_loss_out, float* per_res, float* atoms4, float* axes, float* bound, float* loss_rows,
+                 const uint8_t* owned, int64_t n_total, pp_stream_t stream);
+int pp_prox_loss(const float* loss_rows, int64_t B, int64_t L, int64_t S, const int32_t* n_res, float lamda,
+                 int64_t n_total, float* loss_out, pp_stream_t stream);
+/* Slab-partitioned complex (one rank per slab): B = S = 1, the arrays hold the rank's owned
+ * residues plus the halo; owned uint8 [L] (NULL = all) marks the residues this rank optimises and counts in the
+ * loss, n_total is the residue count of the whole complex (0 = per-complex counts).  pp_prox_init_from_mean builds
+ * mask / z / x from per_res and the all-reduced mean[1]. */
 int pp_prox_init_from_mean(const float* per_res, const float* mean, const float* sc_d, const uint8_t* owned, int64_t G,
                            uint8_t* mask, float* z, float* x, float* m, float* v, pp_stream_t stream);
 
-/* Diagnostics: one 128 x 128 tile D = A W^T on the tcgen05 tensor cores (A [128][K], W [128][K], K % 32 == 0),
- * (kind::tf32: the first tensor-core implementation, kept as a probe) passes 1 = TF32, 3 = split TF32 (~fp32);
- * ts_mode != 0 feeds A from tensor memory instead of shared memory.
- * Pins the descriptor encodings the fused tensor-core kernels rely on (tests/test_gpu_umma.py). */
-int pp_selftest_umma(const float* A, const float* W, float* D, int64_t K, int64_t passes, int64_t ts_mode,
-                     pp_stream_t stream);
-/* Same tile through kind::f16 with fp16 (hi, lo) operand pairs (the format the fused kernels use): passes 1 = plain
+/* Diagnostics: one 128 x 128 tile D = A W^T on the tcgen05 tensor cores (A [128][K], W [128][K], K % 32 == 0)
+ * through kind::f16 with fp16 (hi, lo) operand pairs (the format the fused kernels use): passes 1 = plain
  * fp16 inputs, 3 = split fp16 (~fp32).  ts_mode 1 feeds A from tensor memory as packed fp16 pairs; ts_mode 2 starts
  * a fresh accumulator for every K = 16 step and sums the steps in fp32 with round-to-nearest ("promotion", the scheme
  * of pp_ipmp_node_post_tc32), which removes the bias of the tensor core's truncating fp32 accumulation. */

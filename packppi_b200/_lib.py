@@ -27,7 +27,6 @@ SIGNATURES = {
     "pp_ipmp_node_post": "p" "i" "ppppp" "iii" "pp" "s",
     "pp_ipmp_edge_edge": "p" "i" "pppp" "iii" "p" "i" "pppp" "s",
     "pp_ipmp_edge_tc": "p" "ii" "ppppp" "iii" "p" "i" "pppp" "ii" "s",
-    "pp_ipmp_node_post_tc": "p" "i" "ppp" "iii" "pp" "ii" "s",
     "pp_ipmp_node_pre_tc": "p" "ii" "pp" "ii" "pppp" "s",
     "pp_ipmp_node_post_tc32": "p" "i" "ppp" "iii" "pp" "s",
     "pp_decode_step": "pp" "ii" "p" "i" "ff" "ppp" "ppp" "f" "s",
@@ -36,11 +35,11 @@ SIGNATURES = {
     "pp_clash_reach": "pppp" "i" "p" "s",
     "pp_clash_neighbours_cells": "ppp" "ii" "ff" "i" "ppp" "pp" "s",
     "pp_clash_fwd_bwd": "ppppppppp" "ii" "ff" "i" "p" "pp" "ppp" "s",
-    "pp_prox_init": "ppppppppp" "i" "ff" "p" "pppp" "pp" "ppp" "p" "s",
-    "pp_prox_step": "ppppppppp" "ppppp" "i" "ffffffff" "ppp" "ppp" "p" "p" "i" "s",
+    "pp_prox_init": "ppppppppp" "iii" "p" "ff" "p" "pppp" "pp" "ppp" "p" "s",
+    "pp_prox_step": "ppppppppp" "ppppp" "iii" "p" "ffffffff" "ppp" "ppp" "p" "p" "i" "s",
+    "pp_prox_loss": "p" "iii" "p" "f" "i" "p" "s",
     "pp_prox_init_from_mean": "pppp" "i" "ppppp" "s",
     "pp_featurize": "pppppp" "ii" "ppp" "pppppppppppppp" "s",
-    "pp_selftest_umma": "ppp" "iii" "s",
     "pp_selftest_umma_f16": "ppp" "iii" "s",
     "pp_selftest_gather4": "p" "iiiiiii" "p" "s",
 }
@@ -50,9 +49,9 @@ _lib = None
 
 # kernels launched per entry point (pp_ipmp_layer: 3, or 5 with the edge update - the caller passes `kernels=`)
 KERNELS = {"pp_knn_build": 1, "pp_knn_build_cells": 5, "pp_geometry_build": 1, "pp_edge_embed": 1, "pp_node_embed": 1, "pp_ipmp_layer": 5,
-           "pp_ipmp_node_pre": 1, "pp_ipmp_edge_node": 1, "pp_ipmp_node_post": 1, "pp_ipmp_edge_edge": 1, "pp_ipmp_edge_tc": 1, "pp_ipmp_node_post_tc": 1, "pp_ipmp_node_pre_tc": 1, "pp_ipmp_node_post_tc32": 1,
+           "pp_ipmp_node_pre": 1, "pp_ipmp_edge_node": 1, "pp_ipmp_node_post": 1, "pp_ipmp_edge_edge": 1, "pp_ipmp_edge_tc": 1, "pp_ipmp_node_pre_tc": 1, "pp_ipmp_node_post_tc32": 1,
            "pp_decode_step": 1, "pp_atom14_fwd": 1, "pp_clash_neighbours": 1, "pp_clash_reach": 1, "pp_clash_neighbours_cells": 5, "pp_clash_fwd_bwd": 2,
-           "pp_prox_init": 4, "pp_prox_step": 3, "pp_prox_init_from_mean": 1, "pp_featurize": 1, "pp_selftest_umma": 1, "pp_selftest_umma_f16": 1, "pp_selftest_gather4": 1}
+           "pp_prox_init": 4, "pp_prox_step": 2, "pp_prox_loss": 1, "pp_prox_init_from_mean": 1, "pp_featurize": 1, "pp_selftest_umma_f16": 1, "pp_selftest_gather4": 1}
 LAUNCHES = 0      # running count of kernels launched through call()
 PROFILE = None    # {entry name: []} -> call() appends (start event, end event, rows) around those entries
 
@@ -71,14 +70,12 @@ def load():
                "pp_tc_pre_stream_floats",
                "pp_knn_cells_max"):
         getattr(lib, fn).restype = _I
-    lib.pp_prox_partial_floats.restype = _I
-    lib.pp_prox_partial_floats.argtypes = [_I]
     lib.pp_layout_entry.argtypes = [_I, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(_I), ctypes.POINTER(_I)]
     for name, sig in SIGNATURES.items():
         f = getattr(lib, name)
         f.restype = ctypes.c_int
         f.argtypes = [_KIND[c] for c in sig]
-    if lib.pp_abi_version() != 1:
+    if lib.pp_abi_version() != 2:
         raise RuntimeError("libpackppi_b200.so: ABI version mismatch, rebuild the extension")
     _lib = lib
     return lib

@@ -117,27 +117,42 @@ def compute_residue_clash(batch, SC_D, violation_tolerance_factor=12., clash_ove
 
 
 def find_clash_mask(batch, SC_D, violation_tolerance_factor, clash_overlap_tolerance):
-    """optimize.py:5-18: residues whose loss exceeds the mean, expanded to the four chi -> bool [B, L, 4]."""
+    """optimize.py:5-18: residues whose loss exceeds the mean of their own complex, expanded to the four chi ->
+    bool [B, L, 4] (the reference handles B = 1; with B > 1 the mean runs over the unpadded residues of each item)."""
     per = compute_residue_clash(batch, SC_D.detach(), violation_tolerance_factor, clash_overlap_tolerance)
-    return (per > per.mean()).unsqueeze(-1).expand(-1, -1, 4)
+    if per.numel() == per.shape[-1]:  # one complex, one sample: the reference's case
+        return (per > per.mean()).unsqueeze(-1).expand(*per.shape, 4)
+    cc = clash_context(batch, violation_tolerance_factor, clash_overlap_tolerance)
+    n_res = cc.n_res()
+    n = n_res.to(per.dtype) if n_res is not None else float(per.shape[-1])
+    mean = per.sum(-1) / n  # padding rows carry no loss
+    return (per > mean.unsqueeze(-1)).unsqueeze(-1).expand(*per.shape, 4)
 
 
 def proximal_optimizer(batch, SC_D, violation_tolerance_factor, clash_overlap_tolerance, lamda, num_steps=50):
     """optimize.py:21-73 -> (list of num_steps tensors [1, L, 4], list of num_steps floats).
 
     The whole loop (rebuild, loss, analytic gradient, Adam, snapshot) runs on the device; the losses are copied
-    to the host once at the end instead of one `.item()` per step."""
-    assert batch.num_proteins == 1
+    to the host once at the end instead of one `.item()` per step.
+
+    Beyond the reference (which asserts one complex, optimize.py:27, and is looped per decoy by its notebooks): a padded
+    batch of B complexes and / or SC_D with a leading sample dimension [S, B, L, 4] optimises all S*B items in the same
+    launches, each against the mean of its own residues; the snapshots then have SC_D's shape and every entry of the
+    loss list is a tensor [S, B] (or [B]) of per-item objectives, equal to what a per-item call returns."""
+    B, L = int(batch.X.shape[0]), int(SC_D.shape[-2])
     if _staged(SC_D):
         d = _STAGE_DEVICE
         on_dev = ComplexBatch(**{k: (batch[k].to(d) if torch.is_tensor(batch[k]) else batch[k]) for k in
                                  ("X", "residue_type", "atom_mask", "residue_index", "BB_D", "num_proteins")})
         snaps, loss_list = proximal_optimizer(on_dev, SC_D.to(d), violation_tolerance_factor,
                                               clash_overlap_tolerance, lamda, num_steps)
-        return [s.cpu() for s in snaps], loss_list
+        return [s.cpu() for s in snaps], ([x.cpu() for x in loss_list] if torch.is_tensor(loss_list[0]) else loss_list)
     _cuda_only(SC_D, "proximal_optimizer")
     cc = clash_context(batch, violation_tolerance_factor, clash_overlap_tolerance)
-    L = SC_D.shape[-2]
     snaps, losses, _ = cc.proximal(SC_D.detach().reshape(-1, 4).to(torch.float32), float(lamda), int(num_steps))
-    loss_list = losses.cpu().tolist()
-    return [snaps[k].reshape(1, L, 4) for k in range(num_steps)], loss_list
+    single = B == 1 and SC_D.numel() == L * 4
+    if single:
+        loss_list = losses[:, 0].cpu().tolist()
+        return [snaps[k].reshape(1, L, 4) for k in range(num_steps)], loss_list
+    lead = SC_D.shape[:-2]  # (B,) or (S, B)
+    return [snaps[k].reshape(*lead, L, 4) for k in range(num_steps)], [losses[k].reshape(*lead) for k in range(num_steps)]

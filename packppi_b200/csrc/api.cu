@@ -6,7 +6,7 @@ namespace pp {
 thread_local char g_last_error[512] = "";
 }
 
-extern "C" int pp_abi_version() { return 1; }
+extern "C" int pp_abi_version() { return 2; }
 
 extern "C" const char* pp_last_error() { return pp::g_last_error; }
 

@@ -86,9 +86,7 @@ struct Args {
   const float *B2, *B3, *LNG, *LNB, *BIN, *BOUT, *LN3G, *LN3B;
   const float* hE_in; int he_shared;
   const float *A, *Nn, *pglob;
-  const float* msum;                 // mean attention mask [G]: 0 marks a padding residue (MODE 2: scales b3)
-  const float *rmask, *hres;         // MODE 2: residue mask [G], residual rows h_V [R][128]
-  float in_scale;                    // MODE 2: 1 / K applied to the summed messages
+  const float* msum;                 // mean attention mask [G]: 0 marks a padding residue
   float* out;             // node path: accsum [R][128]; edge path: hE_out [R][K][128]
   unsigned long long* trace;  // optional: clock64 stamps of one tile of CTA 0 (pp_set_tc_trace), else null
   int trace_it;               // which tile of the CTA (0 = first: the stamps include the prologue)
@@ -167,12 +165,11 @@ __device__ __forceinline__ void ld32(const float* __restrict__ p, float (&d)[32]
 
 // MODE 0: node message (G1, G2, masked sum over K)      tile = 4 residues x 32 edges
 // MODE 1: edge update  (G1, G2, G3, LN, FFN, LN)        tile = 4 residues x 32 edges
-// MODE 2: node epilogue (W3, LN0, FFN, LN1 per residue; reference layers.py:127-132)   tile = 128 residue rows
+// (the per-residue node update W3 / LN0 / FFN / LN1 lives in node_post_tc.cu: it needs promoted accumulation)
 template <int MODE, int PASSES, int CLUSTER>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out) {
   constexpr bool EDGE = MODE != 0;   // runs the G3 / LayerNorm / FFN part
-  constexpr bool POST = MODE == 2;   // per-residue rows instead of per-edge rows, no G1 / G2
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* stage = smem;  // h_E rows of one tile: box (chunk c, residue rl) at ((c * 4 + rl) << 12), row k at k << 7
   uint8_t* Aring = stage + kStageBytes;
@@ -193,7 +190,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int R = a.S * a.G, K = a.K;
-  const int ntiles = POST ? (R + kRows - 1) / kRows : (R + 3) / 4;
+  const int ntiles = (R + 3) / 4;
   // persistent CTAs: every CTA runs the same number of iterations (a cluster shares one weight stream in lockstep);
   // iterations past the last tile work on fully masked rows
   const int niter = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -204,7 +201,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
 #ifndef PP_TC_SKIP
 #define PP_TC_SKIP 1
 #endif
-  constexpr bool SKIP = PP_TC_SKIP && CLUSTER == 1 && !POST;
+  constexpr bool SKIP = PP_TC_SKIP && CLUSTER == 1;
   const int tstep = (int)gridDim.x;
   const int tend = SKIP ? ntiles : niter * tstep;  // tiles of this CTA: blockIdx.x, + tstep, ... < tend
   auto live = [&](int tile) {
@@ -236,7 +233,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
     const float* src[8] = {a.B2, a.B3, a.LNG, a.LNB, a.BIN, a.BOUT, a.LN3G, a.LN3B};
     const int off[9] = {kP_B2, kP_B3, kP_LN2G, kP_LN2B, kP_BIN, kP_BOUT, kP_LN3G, kP_LN3B, kParamFloats};
     for (int t = 0; t < 8; ++t)
-      if ((EDGE || t == 0) && !(POST && t == 0))
+      if (EDGE || t == 0)
         for (int i = tid; i < off[t + 1] - off[t]; i += kThreadsTC) prm[off[t] + i] = src[t][i];
   }
   if (warp == kWarpMMA) tmem_alloc<512>(tmem_slot);
@@ -256,9 +253,9 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
       const uint32_t crank = (CLUSTER > 1) ? cluster_rank() : 0;
       for (int tile = next_tile((int)blockIdx.x); tile < tend; tile = next_tile(tile + tstep)) {
         const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wstream);
-        constexpr int NCHUNK = POST ? 36 : (EDGE ? kChunksEdge : kChunksNode);
+        constexpr int NCHUNK = EDGE ? kChunksEdge : kChunksNode;
         for (int i = 0; i < NCHUNK; ++i) {
-          const int kc = (!POST && i == 5) ? kPairKC : kKC;
+          const int kc = (i == 5) ? kPairKC : kKC;
           const uint32_t img = (uint32_t)kRows * kc * 2;          // hi image; the lo image follows it in the stream
           const uint32_t bytes = img * (PASSES == 3 ? 2 : 1);
           mbar_wait(&b_empty[rb_.idx], rb_.phase);
@@ -276,7 +273,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
       }
     }
   } else if (warp == kWarpTiles) {
-    if (!POST && lane == 0) {
+    if (lane == 0) {
       // ---------------------------------------------------------------- h_E tile loader (TMA)
       // This thread owns the staging buffer.  Node message path: tile t+1 is fetched as soon as the workers have
       // read tile t.  Edge update: the workers read tile it+1, then write the result rows of tile it into the buffer;
@@ -368,10 +365,9 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
         else chunk_kc(std::integral_constant<int, kPairKC>{}, ss, acc, a_tm, fresh);
       };
       auto wait_workers = [&]() { mbar_wait(wk_done, wk_phase); wk_phase ^= 1; fence_after_sync(); };
-      // first GEMM of a tile: G1 = [h_E | pair] (176 wide) of the message MLP, or W3 of the node epilogue
+      // first GEMM of a tile: G1 = [h_E | pair] (176 wide) of the message MLP
       auto head = [&](uint32_t acc, int bar) {
-        if (!POST) { for (int c = 0; c < 6; ++c) chunk(true, acc, 0, c == 5 ? kPairKC : kKC, c == 0); }
-        else       { for (int c = 0; c < 4; ++c) chunk(true, acc, 0, kKC, c == 0); }
+        for (int c = 0; c < 6; ++c) chunk(true, acc, 0, c == 5 ? kPairKC : kKC, c == 0);
         commit_acc(bar);
       };
       // Tiles are software-pipelined: the head GEMM of tile it+1 is issued before the workers run the last epilogue of
@@ -390,19 +386,15 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
         if (it > 0) {  // the previous tile has been read out completely: its X (this tile's Y) may be overwritten
           mbar_wait(tile_done, td_phase); td_phase ^= 1; fence_after_sync();
         }
-        if (!POST) {
-          for (int c = 0; c < 4; ++c) chunk(true, Y, 0, kKC, c == 0);  // G2
-          commit_acc(yb);
-        }
+        for (int c = 0; c < 4; ++c) chunk(true, Y, 0, kKC, c == 0);  // G2
+        commit_acc(yb);
         if (!EDGE) {
           // G2's operand chunks exist only once every worker has drained ACC0, so the next G1 may follow directly
           if (more) head(ACC0, 0);
           continue;
         }
-        if (!POST) {
-          for (int c = 0; c < 4; ++c) chunk(true, X, 0, kKC, c == 0);  // G3
-          commit_acc(xb);
-        }
+        for (int c = 0; c < 4; ++c) chunk(true, X, 0, kKC, c == 0);  // G3
+        commit_acc(xb);
         // FFN, software-pipelined by one slice: while the workers turn slice j into the A operand of FFN-out j,
         // the tensor pipe runs FFN-out j-1 and FFN-in j+1
         wait_workers();  // e is in TMEM, X / Y are drained
@@ -432,7 +424,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
     uint32_t accph[2] = {0, 0};
     const float* wsc = a.wstream + kImageFloats;  // 1 / scale of the weight images
     const float sG1 = wsc[0], sG2 = wsc[1], sG3 = wsc[2], sFI = wsc[3], sFO = wsc[4];
-    constexpr int kChunksTile = POST ? 20 : (EDGE ? 30 : 10);  // A chunks per tile
+    constexpr int kChunksTile = EDGE ? 30 : 10;  // A chunks per tile
     const bool tracer = a.trace && blockIdx.x == 0 && tid == 0;
     int stamp_i = 0;
     auto stamp = [&](bool first_tile) {
@@ -446,16 +438,6 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
     };
     auto row_ctx = [&](int tile) {
       RowCtx c;
-      if (POST) {  // one residue row per thread
-        c.r = tile * kRows + m;
-        c.in_range = c.r < R;
-        c.rr = min(c.r, R - 1);
-        c.g = c.rr % a.G;
-        c.on = c.in_range && a.rmask[c.g] != 0.f;
-        c.jrow = c.rr;
-        c.hrow = a.hE_in + (size_t)c.rr * 128;  // summed messages of the residue
-        return c;
-      }
       c.r = tile * 4 + rl;
       c.in_range = c.r < R && k < K;
       c.rr = min(c.r, R - 1);
@@ -500,8 +482,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
       tmem_st32(col + lane_base, u);
     };
 
-    // ---- first A operand of a tile (chunks qb .. qb+5): h_E row (4 chunks) and the pair geometry (32 + 16 columns);
-    //      node epilogue: the residue's summed messages scaled by 1/K (the mean over K commutes with W3), 4 chunks.
+    // ---- first A operand of a tile (chunks qb .. qb+5): h_E row (4 chunks) and the pair geometry (32 + 16 columns).
     //      Edge update: the raw row is also parked in the TMEM region `stash` for the residual, instead of reading
     //      it from global memory a second time (a row-per-thread read costs 32 L1 wavefronts per instruction).
     //      `release`: the staging buffer is handed back to the loader once the rows have been consumed (node message
@@ -509,34 +490,13 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
     auto first_operand = [&](const RowCtx& c, int qb, uint32_t stash, bool release) {
       float v[32];
       float4 h[kCPT][8];
-      if (POST) {
+      mbar_wait(stage_full, sf_phase); sf_phase ^= 1;
 #pragma unroll
-        for (int t = 0; t < kCPT; ++t)
+      for (int t = 0; t < kCPT; ++t)
 #pragma unroll
-          for (int u = 0; u < 8; ++u)
-            h[t][u] = c.in_range ? *reinterpret_cast<const float4*>(c.hrow + (grp + kGroups * t) * 32 + u * 4)
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-      } else {
-        mbar_wait(stage_full, sf_phase); sf_phase ^= 1;
-#pragma unroll
-        for (int t = 0; t < kCPT; ++t)
-#pragma unroll
-          for (int u = 0; u < 8; ++u)
-            h[t][u] = c.in_range ? *reinterpret_cast<const float4*>(srow + ((grp + kGroups * t) << 14) + ((u ^ swz) << 4))
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      if (POST) {
-#pragma unroll
-        for (int t = 0; t < kCPT; ++t) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            v[u * 4] = h[t][u].x * a.in_scale; v[u * 4 + 1] = h[t][u].y * a.in_scale;
-            v[u * 4 + 2] = h[t][u].z * a.in_scale; v[u * 4 + 3] = h[t][u].w * a.in_scale;
-          }
-          publish(qb + grp + kGroups * t, v, kKC);
-        }
-        return;
-      }
+        for (int u = 0; u < 8; ++u)
+          h[t][u] = c.in_range ? *reinterpret_cast<const float4*>(srow + ((grp + kGroups * t) << 14) + ((u ^ swz) << 4))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
       const float4* fr4 = reinterpret_cast<const float4*>(a.geo + (size_t)c.g * PP_GEO_STRIDE);
       const float4* pi4 = reinterpret_cast<const float4*>(a.pglob + (size_t)c.rr * 24);
       const float4* pj4 = reinterpret_cast<const float4*>(a.pglob + (size_t)c.jrow * 24);
@@ -621,7 +581,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
       float v[32];
 
       // ---- epilogue of the head GEMM G1: x1 = relu(acc + A_i + N_j); the two gathered rows are fetched before the wait
-      if (!POST) {
+      {
         const float* Ai = a.A + (size_t)rr * 128;
         const float* Nj = a.Nn + (size_t)cx.jrow * 128;
         float4 an[kCPT][8];
@@ -682,7 +642,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
         stamp(t0);  // 5: sums written
       } else {
         // ---- epilogue of G2: x2 = relu(acc + b2)
-        if (!POST) {
+        {
           mbar_wait(&acc_full[yb], accph[yb]); accph[yb] ^= 1;
           fence_after_sync();
           stamp(t0);  // 4: G2 complete
@@ -699,16 +659,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
         }
         // ---- epilogue of G3: e = LN2(h_E + mask * (acc + b3))   (layers.py:139-142); e -> TMEM (fp32 and packed fp16)
         {
-          float4 h[kCPT][8];
-          if (POST) {  // residual = h_V of the residue; b3 enters scaled by the mean attention mask (layers.py:125-128)
-            const float* hv = a.hres + (size_t)rr * 128;
-#pragma unroll
-            for (int t = 0; t < kCPT; ++t)
-#pragma unroll
-              for (int u = 0; u < 8; ++u) h[t][u] = *reinterpret_cast<const float4*>(hv + (grp + kGroups * t) * 32 + u * 4);
-          }
-          const float bscale = POST ? a.msum[cx.g] : 1.f;
-          const bool gate = POST ? true : on;
+          const bool gate = on;
           mbar_wait(&acc_full[xb], accph[xb]); accph[xb] ^= 1;
           fence_after_sync();
           stamp(t0);  // 6: G3 complete
@@ -717,19 +668,12 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
 #pragma unroll
           for (int t = 0; t < kCPT; ++t) {
             const int c = grp + kGroups * t;
-            if (POST) {
-#pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                x[t][u * 4] = h[t][u].x; x[t][u * 4 + 1] = h[t][u].y; x[t][u * 4 + 2] = h[t][u].z; x[t][u * 4 + 3] = h[t][u].w;
-              }
-            } else {
-              load_acc(RE, c, x[t]);  // the raw h_E row parked by first_operand
-            }
+            load_acc(RE, c, x[t]);  // the raw h_E row parked by first_operand
             load_acc(X, c, v);
             const float* b = prm + kP_B3 + c * 32;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              x[t][i] += gate ? fmaf(v[i], sG3, b[i] * bscale) : 0.f;
+              x[t][i] += gate ? fmaf(v[i], sG3, b[i]) : 0.f;
               sum += x[t][i];
             }
           }
@@ -777,7 +721,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
             const float* b = prm + kP_BIN + j * 128 + c * 32;
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(fmaf(t ? v2[i] : v[i], sFI, b[i]), 0.f);
-            publish(qbase + (POST ? 4 : 14) + 4 * j + c, v, kKC);
+            publish(qbase + 14 + 4 * j + c, v, kKC);
           }
           stamp(t0);  // 9 + 2j: hidden slice j published
         }
@@ -807,10 +751,9 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
 #pragma unroll
           for (int i = 0; i < 32; ++i) { float d = y[t][i] - mean3; var += d * d; }
         const float rstd3 = rsqrtf(row_total(var, 3) * (1.f / 128.f) + 1e-5f);
-        // node epilogue: one row per thread straight to global memory; edge update: into the staging buffer (every
-        // worker has read the next tile's rows out of it: the row_total barriers above come after first_operand)
-        float* orow = a.out + (size_t)rr * 128;
-        if (in_range || !POST) {
+        // result rows go into the staging buffer (every worker has read the next tile's rows out of it: the row_total
+        // barriers above come after first_operand)
+        {
 #pragma unroll
           for (int t = 0; t < kCPT; ++t) {
             const int c = grp + kGroups * t;
@@ -824,15 +767,12 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
               o.y = on ? (y[t][i + 1] - mean3) * rstd3 * gm[i + 1] + bt[i + 1] : 0.f;
               o.z = on ? (y[t][i + 2] - mean3) * rstd3 * gm[i + 2] + bt[i + 2] : 0.f;
               o.w = on ? (y[t][i + 3] - mean3) * rstd3 * gm[i + 3] + bt[i + 3] : 0.f;
-              if (POST) *reinterpret_cast<float4*>(orow + c * 32 + i) = o;
-              else *reinterpret_cast<float4*>(srow + (c << 14) + ((u ^ swz) << 4)) = o;
+              *reinterpret_cast<float4*>(srow + (c << 14) + ((u ^ swz) << 4)) = o;
             }
           }
         }
-        if (!POST) {  // hand the rows to the tile loader's TMA stores
-          fence_async_smem();
-          mbar_arrive(stage_free);
-        }
+        fence_async_smem();  // hand the rows to the tile loader's TMA stores
+        mbar_arrive(stage_free);
         stamp(t0);  // 18: outputs written
       }
       // end of tile: this thread has read everything the tile left in TMEM
@@ -894,9 +834,9 @@ static int launch(const Args& a, cudaStream_t stream) {
   alignas(64) CUtensorMap tm_in, tm_out;
   memset(&tm_in, 0, sizeof(tm_in));
   memset(&tm_out, 0, sizeof(tm_out));
-  if (MODE != 2 && make_row_map(&tm_in, a.hE_in, a.he_shared ? a.G : R, a.K)) return 1;
+  if (make_row_map(&tm_in, a.hE_in, a.he_shared ? a.G : R, a.K)) return 1;
   if (MODE == 1 && make_row_map(&tm_out, a.out, R, a.K)) return 1;
-  unsigned tiles = (MODE == 2) ? (unsigned)((R + kRows - 1) / kRows) : (unsigned)((R + 3) / 4);
+  unsigned tiles = (unsigned)((R + 3) / 4);
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
@@ -949,7 +889,7 @@ extern "C" int pp_set_tc_trace(uint64_t* trace) {
 
 // Tensor-core version of pp_ipmp_edge_node (path = 0) and pp_ipmp_edge_edge (path = 1).
 //   wstream: operand images of this layer and path, pp_tc_stream_floats() floats (weights.py: pack_tc_stream)
-//   passes : 3 = split fp16 (fp32-grade), 1 = plain fp16 inputs;  cluster: 1, 2 or 4 CTAs sharing the weight stream
+//   passes : 3 = split fp16 (fp32-grade), 1 = plain fp16 inputs;  cluster: 1 or 2 CTAs sharing the weight stream
 //   out    : accsum [S*G][128] (path 0) or hE_out [S*G][K][128] (path 1, may alias hE_in when he_shared == 0)
 extern "C" int pp_ipmp_edge_tc(const float* weights, int64_t layer, int64_t path, const float* wstream,
                                const float* geo, const int32_t* nbr, const float* mask_attend, const float* msum,
@@ -960,7 +900,7 @@ extern "C" int pp_ipmp_edge_tc(const float* weights, int64_t layer, int64_t path
   PP_REQUIRE(layer >= 0 && layer < 3 && (path == 0 || path == 1), "layer / path out of range");
   PP_REQUIRE(G > 0 && S > 0 && K > 0 && K <= PP_KMAX, "bad sizes");
   PP_REQUIRE(passes == 1 || passes == 3, "passes must be 1 or 3");
-  PP_REQUIRE(cluster == 1 || cluster == 2 || cluster == 4, "cluster must be 1, 2 or 4");
+  PP_REQUIRE(cluster == 1 || cluster == 2, "cluster must be 1 or 2");
   const float* Lb = weights + layer * wl::kLayerStride;
   tc::Args a{};
   a.geo = geo; a.nbr = nbr; a.matt = mask_attend; a.msum = msum;
@@ -978,42 +918,10 @@ extern "C" int pp_ipmp_edge_tc(const float* weights, int64_t layer, int64_t path
   a.trace_it = g_tc_trace_it;
   int rc;
 #define PP_TC_CASE(E, P, C) if (path == (E) && passes == (P) && cluster == (C)) rc = tc::launch<E, P, C>(a, stream); else
-  PP_TC_CASE(0, 3, 1) PP_TC_CASE(0, 3, 2) PP_TC_CASE(0, 3, 4) PP_TC_CASE(0, 1, 1) PP_TC_CASE(0, 1, 2) PP_TC_CASE(0, 1, 4)
-  PP_TC_CASE(1, 3, 1) PP_TC_CASE(1, 3, 2) PP_TC_CASE(1, 3, 4) PP_TC_CASE(1, 1, 1) PP_TC_CASE(1, 1, 2) PP_TC_CASE(1, 1, 4)
-  rc = 2;
-  if (rc) return rc;
-  return check_launch("pp_ipmp_edge_tc");
-}
-
-// Tensor-core version of pp_ipmp_node_post: h_V <- mask * LN1(e + FFN(e)), e = LN0(h_V + W3 mean_k(msg) + b3 mean_k(mask))
-// (reference layers.py:127-132).  wstream = operand images of path 2 of this layer; hV [S*G][128] is updated in place.
-extern "C" int pp_ipmp_node_post_tc(const float* weights, int64_t layer, const float* wstream, const float* msum,
-                                    const float* residue_mask, int64_t G, int64_t K, int64_t S, const float* wsAcc,
-                                    float* hV, int64_t passes, int64_t cluster, cudaStream_t stream) {
-  PP_REQUIRE(weights && wstream && msum && residue_mask && wsAcc && hV, "null pointer");
-  PP_REQUIRE(layer >= 0 && layer < 3, "layer out of range");
-  PP_REQUIRE(G > 0 && S > 0 && K > 0 && K <= PP_KMAX, "bad sizes");
-  PP_REQUIRE(passes == 1 || passes == 3, "passes must be 1 or 3");
-  PP_REQUIRE(cluster == 1 || cluster == 2 || cluster == 4, "cluster must be 1, 2 or 4");
-  const float* Lb = weights + layer * wl::kLayerStride;
-  tc::Args a{};
-  a.G = (int)G; a.K = (int)K; a.S = (int)S;
-  a.wstream = wstream;
-  a.B2 = Lb + PP_OFF(L0_N_B2);
-  a.B3 = Lb + PP_OFF(L0_N_B3);
-  a.LNG = Lb + PP_OFF(L0_LN0_G); a.LNB = Lb + PP_OFF(L0_LN0_B);
-  a.BIN = Lb + PP_OFF(L0_NF_BIN); a.BOUT = Lb + PP_OFF(L0_NF_BOUT);
-  a.LN3G = Lb + PP_OFF(L0_LN1_G); a.LN3B = Lb + PP_OFF(L0_LN1_B);
-  a.hE_in = wsAcc; a.he_shared = 0;
-  a.rmask = residue_mask; a.msum = msum; a.hres = hV;
-  a.in_scale = 1.f / (float)K;
-  a.out = hV;
-  a.trace = nullptr;
-  const int64_t path = 2;
-  int rc;
-  PP_TC_CASE(2, 3, 1) PP_TC_CASE(2, 3, 2) PP_TC_CASE(2, 3, 4) PP_TC_CASE(2, 1, 1) PP_TC_CASE(2, 1, 2) PP_TC_CASE(2, 1, 4)
+  PP_TC_CASE(0, 3, 1) PP_TC_CASE(0, 3, 2) PP_TC_CASE(0, 1, 1) PP_TC_CASE(0, 1, 2)
+  PP_TC_CASE(1, 3, 1) PP_TC_CASE(1, 3, 2) PP_TC_CASE(1, 1, 1) PP_TC_CASE(1, 1, 2)
   rc = 2;
 #undef PP_TC_CASE
   if (rc) return rc;
-  return check_launch("pp_ipmp_node_post_tc");
+  return check_launch("pp_ipmp_edge_tc");
 }

@@ -35,15 +35,33 @@ __device__ __forceinline__ void mat_vec(const float* A, const float* v, float* o
   for (int i = 0; i < 3; ++i) o[i] = A[i * 3] * v[0] + A[i * 3 + 1] * v[1] + A[i * 3 + 2] * v[2];
 }
 
+// Optional tail of an atom14 launch in the proximal loop: blocks first .. first + items - 1 reduce the objective of the
+// PREVIOUS step from its per-row terms (one launch less per step; the rows are rewritten only by the next pair kernel).
+struct ReduceArgs {
+  const float* loss_rows;  // null: no reduction in this launch
+  int first, B, L;
+  const int* n_res;
+  float lamda, inv_n_total;
+  float* out;
+};
+__device__ void prox_reduce_item(const float* __restrict__ loss_rows, int it, int B, int L, const int* __restrict__ n_res,
+                                 float lamda, float inv_n_total, float* __restrict__ out, float (*sh)[128]);
+
 // tbl record: [0:48) chi1..4 default frames 3x4 | [48:90) literature positions | [90:104) group | [104:118) ideal mask
 //             | [118:132) clash radius | [132] reach
-__global__ void atom14_kernel(const float* __restrict__ tbl, const float* __restrict__ X,
+__global__ void __launch_bounds__(128) atom14_kernel(const float* __restrict__ tbl, const float* __restrict__ X,
                               const long long* __restrict__ residue_type, const float* __restrict__ chi,
                               const float* __restrict__ chi_alt, const unsigned char* __restrict__ use_alt, int G, int S,
                               float* __restrict__ xyz_out /*[R][14][3] or null*/,
                               const float* __restrict__ atom_exists /*[G][14] or null*/,
                               float4* __restrict__ atoms4 /*[R][14] or null*/, float* __restrict__ axes /*[R][4][6] or null*/,
-                              float* __restrict__ bound /*[R] current max |CA - atom| or null*/) {
+                              float* __restrict__ bound /*[R] current max |CA - atom| or null*/, ReduceArgs red) {
+  if (red.loss_rows && (int)blockIdx.x >= red.first) {
+    __shared__ float sh[2][128];
+    prox_reduce_item(red.loss_rows, (int)blockIdx.x - red.first, red.B, red.L, red.n_res, red.lamda, red.inv_n_total,
+                     red.out, sh);
+    return;
+  }
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= S * G) return;
   int g = r % G;
@@ -213,18 +231,23 @@ struct AdamArgs {
   const unsigned char* mask;  // [R][4] clash mask
   float* snapshot;      // [R][4] where(mask, x_new, SC_D)
   const unsigned char* owned;  // [R] or null: residues this rank owns (slab-partitioned complex); others are halo
-  float step_size, bc2_sqrt, beta1, beta2, eps, inv_n;
+  float step_size, bc2_sqrt, beta1, beta2, eps;
+  float lamda;
+  float inv_n_total;    // > 0: 1 / residues of the whole complex (slab-partitioned); else 1 / n_res[complex of the row]
+  const int* n_res;     // [B] residues per complex of a padded batch (rows l >= n_res[b] are padding)
+  int L;                // padded length: complex of residue g is g / L
+  float* loss_rows;     // [R][2] per-row terms of the objective: (clash per residue, sum_k (x' - z)^2), 0 if not counted
 };
 
 template <int MODE>  // 0: loss only   1: loss + dL/dchi   2: proximal step (loss, gradient, Adam update)
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)
 clash_pair_kernel(const float4* __restrict__ atoms, const float* __restrict__ bound, const float* __restrict__ axes,
                   const float* __restrict__ X, const long long* __restrict__ residue_type,
                   const float* __restrict__ atom_exists, const long long* __restrict__ nbr_start,
                   const int* __restrict__ nbr_list, const float* __restrict__ lower, const float* __restrict__ upper,
                   const float* __restrict__ tbl, const float* __restrict__ res_w /*[R] upstream weight or null*/,
-                  float w_uniform, float tol, float max_cut, int G, int S, float* __restrict__ per_res /*[R]*/,
-                  float* __restrict__ grad_chi /*[R][4]*/, AdamArgs ad, float* __restrict__ partial /*[gridDim][2]*/) {
+                  float tol, float max_cut, int G, int S, float* __restrict__ per_res /*[R]*/,
+                  float* __restrict__ grad_chi /*[R][4]*/, AdamArgs ad) {
   const int lane16 = threadIdx.x & 15;
   const int half = (threadIdx.x >> 4) & 1;  // which entries of the neighbour list this half-warp takes
   const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -242,6 +265,13 @@ clash_pair_kernel(const float4* __restrict__ atoms, const float* __restrict__ bo
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) nsc += __shfl_xor_sync(0xffffffffu, nsc, o);
   const float inv_i = 1.f / (1e-10f + nsc);
+  // proximal step: the clash term enters the objective as lamda * mean over the residues of the row's own complex
+  float inv_n = 0.f;
+  if (MODE == 2) {
+    const int cb = g / ad.L;
+    inv_n = ad.inv_n_total > 0.f ? ad.inv_n_total : 1.f / (float)(ad.n_res ? ad.n_res[cb] : ad.L);
+  }
+  const float w_uniform = ad.lamda * inv_n;
   const float wi = (MODE == 0) ? 0.f : ((res_w ? res_w[rr] : w_uniform) * inv_i);
 
   float loss = 0.f, fx = 0.f, fy = 0.f, fz = 0.f;
@@ -249,40 +279,70 @@ clash_pair_kernel(const float4* __restrict__ atoms, const float* __restrict__ bo
   const float bi = bound[rr];
 
   // ---- between residues (clash.py:102-254)
-  long long n0 = nbr_start[g], n1 = nbr_start[g + 1];
-  for (long long n = n0 + half; n < n1; n += 2) {
-    int gj = nbr_list[n];
-    int rj = s * G + gj;
-    float dx = X[(size_t)gj * 42 + 3] - cax, dy = X[(size_t)gj * 42 + 4] - cay, dz = X[(size_t)gj * 42 + 5] - caz;
-    float lim = bi + bound[rj] + max_cut;
-    if (dx * dx + dy * dy + dz * dz >= lim * lim) continue;  // uniform across the 16 lanes of the residue
-    float wj = 0.f;
-    if (MODE != 0) {
-      float nj = 0.f;
+  // The neighbour list (static, built from worst-case extents) is pruned against the CURRENT bounding spheres 32
+  // entries at a time, one entry per lane (the loads of a chunk are independent); the survivors are then visited in
+  // list order, the two half-warps taking them alternately, with all 14 atom records of a survivor fetched at once.
+  const long long n0 = nbr_start[g], n1 = nbr_start[g + 1];
+  const int lane = threadIdx.x & 31;
+  for (long long nb = n0; nb < n1; nb += 32) {
+    const long long idx = nb + lane;
+    int gj_l = 0;
+    float wj_l = 0.f;
+    bool pass = false;
+    if (idx < n1) {
+      gj_l = nbr_list[idx];
+      const float dx = X[(size_t)gj_l * 42 + 3] - cax, dy = X[(size_t)gj_l * 42 + 4] - cay, dz = X[(size_t)gj_l * 42 + 5] - caz;
+      const float lim = bi + bound[s * G + gj_l] + max_cut;
+      pass = dx * dx + dy * dy + dz * dz < lim * lim;
+      if (MODE != 0 && pass) {
+        float nj = 0.f;
 #pragma unroll
-      for (int b = 4; b < 14; ++b) nj += atom_exists[(size_t)gj * 14 + b];
-      wj = (res_w ? res_w[rj] : w_uniform) / (1e-10f + nj);
+        for (int b = 4; b < 14; ++b) nj += atom_exists[(size_t)gj_l * 14 + b];
+        wj_l = (res_w ? res_w[s * G + gj_l] : w_uniform) / (1e-10f + nj);
+      }
     }
-    const float4* pj = atoms + (size_t)rj * 14;
+    unsigned surv = __ballot_sync(0xffffffffu, pass);
+    while (surv) {
+      // two survivors per round, one for each half-warp: uniform control flow (only a trailing odd survivor leaves
+      // the second half-warp idle)
+      const int s0 = __ffs(surv) - 1;
+      surv &= surv - 1;
+      const int s1 = surv ? __ffs(surv) - 1 : -1;
+      if (surv) surv &= surv - 1;
+      const int src = half ? s1 : s0;
+      const int gj = __shfl_sync(0xffffffffu, gj_l, src < 0 ? 0 : src);
+      const float wj = __shfl_sync(0xffffffffu, wj_l, src < 0 ? 0 : src);
+      if (src < 0) continue;
+      const float4* pj = atoms + (size_t)(s * G + gj) * 14;
 #pragma unroll
-    for (int b = 0; b < 14; ++b) {
-      float4 q = pj[b];
-      bool ok = ea && q.w != 0.f && !(a < 4 && b < 4) && !(a == 5 && b == 5);
-      float ex = pa.x - q.x, ey = pa.y - q.y, ez = pa.z - q.z;
-      float d = sqrtf(1e-10f + (ex * ex + ey * ey + ez * ez));
-      float e = __fsub_rn(__fsub_rn(__fadd_rn(pa.w, q.w), tol), d);  // (r_a + r_b) - tol - d
-      if (ok && e > 0.f) {
-        loss += e;
-        if (MODE != 0) {
-          float c = ((a >= 4) ? wi : 0.f) + ((b >= 4) ? wj : 0.f);
-          float sc = -c / d;  // d e / d p_a = -(p_a - p_b) / d
-          fx += sc * ex; fy += sc * ey; fz += sc * ez;
+      for (int b0 = 0; b0 < 14; b0 += 7) {
+        float4 q[7];
+#pragma unroll
+        for (int b = 0; b < 7; ++b) q[b] = pj[b0 + b];
+#pragma unroll
+        for (int bb = 0; bb < 7; ++bb) {
+          const int b = b0 + bb;
+          const float ex = pa.x - q[bb].x, ey = pa.y - q[bb].y, ez = pa.z - q[bb].z;
+          const float d2 = ex * ex + ey * ey + ez * ez;
+          const float lim = pa.w + q[bb].w - tol;
+          // cheap conservative reject (no sqrt): e = lim - sqrt(1e-10 + d2) can only be positive if d2 < lim^2
+          if (d2 > lim * lim * 1.0001f || lim <= 0.f) continue;
+          const bool ok = ea && q[bb].w != 0.f && !(a < 4 && b < 4) && !(a == 5 && b == 5);
+          const float d = sqrtf(1e-10f + d2);
+          const float e = __fsub_rn(__fsub_rn(__fadd_rn(pa.w, q[bb].w), tol), d);  // (r_a + r_b) - tol - d
+          if (ok && e > 0.f) {
+            loss += e;
+            if (MODE != 0) {
+              const float c = ((a >= 4) ? wi : 0.f) + ((b >= 4) ? wj : 0.f);
+              const float sc = -c / d;  // d e / d p_a = -(p_a - p_b) / d
+              fx += sc * ex; fy += sc * ey; fz += sc * ez;
+            }
+          }
         }
       }
     }
   }
-  // the two halves of the neighbour list (fixed order: even entries + odd entries); both half-warps continue with
-  // the totals
+  // the two halves of the survivors (fixed order: even + odd); both half-warps continue with the totals
   loss += __shfl_xor_sync(0xffffffffu, loss, 16);
   fx += __shfl_xor_sync(0xffffffffu, fx, 16);
   fy += __shfl_xor_sync(0xffffffffu, fy, 16);
@@ -356,7 +416,7 @@ clash_pair_kernel(const float4* __restrict__ atoms, const float* __restrict__ bo
       float diff = xp - z;
       sc_term = diff * diff;
       float gcl = (lane16 == 0) ? gk[0] : (lane16 == 1) ? gk[1] : (lane16 == 2) ? gk[2] : gk[3];
-      float grad = mk ? (2.f * diff * ad.inv_n + gcl) : 0.f;
+      float grad = mk ? (2.f * diff * inv_n + gcl) : 0.f;
       float m = ad.beta1 * ad.m[o] + (1.f - ad.beta1) * grad;
       float v = ad.beta2 * ad.v[o] + (1.f - ad.beta2) * grad * grad;
       float xn = x - ad.step_size * m / (sqrtf(v) / ad.bc2_sqrt + ad.eps);
@@ -369,49 +429,55 @@ clash_pair_kernel(const float4* __restrict__ atoms, const float* __restrict__ bo
     sc_term += __shfl_xor_sync(0xffffffffu, sc_term, 1);
     sc_term += __shfl_xor_sync(0xffffffffu, sc_term, 2);
   }
-  const bool counted = (MODE != 2 || ad.owned == nullptr) ? true : (ad.owned[rr] != 0);
-  if (partial) {
-    // block partial sums (fixed order): [0] sum of per-residue clash, [1] sum of |x' - z|^2
-    __shared__ float red[2][4];
-    if (lane16 == 0 && half == 0) {
-      red[0][threadIdx.x >> 5] = (live && counted) ? pr : 0.f;
-      red[1][threadIdx.x >> 5] = (live && counted) ? sc_term : 0.f;
-    }
-    __syncthreads();
-    if (threadIdx.x < 2) {
-      float t = 0.f;
-      for (int i = 0; i < 4; ++i) t += red[threadIdx.x][i];
-      partial[(size_t)blockIdx.x * 2 + threadIdx.x] = t;
-    }
+  if (MODE != 1 && ad.loss_rows && live && lane16 == 0 && half == 0) {
+    const bool counted = ad.owned == nullptr || ad.owned[rr] != 0;
+    ad.loss_rows[(size_t)r * 2] = counted ? pr : 0.f;
+    ad.loss_rows[(size_t)r * 2 + 1] = counted ? sc_term : 0.f;
   }
 }
 
-// loss[0] = lamda * sum(clash)/n + sum(sc)/n ; also mean clash in loss[1]   (single block, fixed order)
-__global__ void prox_reduce_kernel(const float* __restrict__ partial, int nblocks, float lamda, float inv_n,
-                                   float* __restrict__ out) {
-  __shared__ float sh[2][256];
-  float a = 0.f, b = 0.f;
-  for (int i = threadIdx.x; i < nblocks; i += 256) { a += partial[2 * i]; b += partial[2 * i + 1]; }
-  sh[0][threadIdx.x] = a;
-  sh[1][threadIdx.x] = b;
+// Objective of one (sample, complex) item from its per-row terms, fixed summation order (128 threads):
+//   out[0] = sum_rows |x' - z|^2 / n + lamda * sum_rows clash / n   (optimize.py:37-45),  out[1] = mean clash.
+// Item it = s * B + b owns rows s * G + b * L + [0, n_res[b]).
+__device__ void prox_reduce_item(const float* __restrict__ loss_rows, int it, int B, int L, const int* __restrict__ n_res,
+                                 float lamda, float inv_n_total, float* __restrict__ out, float (*sh)[128]) {
+  const int s = it / B, b = it - s * B;
+  const int n = n_res ? n_res[b] : L;
+  const float* rows = loss_rows + ((size_t)s * B * L + (size_t)b * L) * 2;
+  float c = 0.f, q = 0.f;
+  for (int i = threadIdx.x; i < n; i += 128) { c += rows[2 * i]; q += rows[2 * i + 1]; }
+  sh[0][threadIdx.x] = c;
+  sh[1][threadIdx.x] = q;
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) { sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; }
+  for (int o = 64; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) { sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    out[0] = sh[1][0] * inv_n + lamda * (sh[0][0] * inv_n);
-    out[1] = sh[0][0] * inv_n;
+    const float inv_n = inv_n_total > 0.f ? inv_n_total : 1.f / (float)n;
+    out[(size_t)it * 2] = sh[1][0] * inv_n + lamda * (sh[0][0] * inv_n);
+    out[(size_t)it * 2 + 1] = sh[0][0] * inv_n;
   }
 }
 
-// mask = per_res > mean(per_res), expanded to the 4 chi; z = SC_D * mask; x = z; m = v = 0   (optimize.py:5-31,47)
-__global__ void prox_init_kernel(const float* __restrict__ per_res, const float* __restrict__ mean, const float* __restrict__ sc_d,
-                                 int R, const unsigned char* __restrict__ owned, unsigned char* __restrict__ mask,
-                                 float* __restrict__ z, float* __restrict__ x, float* __restrict__ m, float* __restrict__ v) {
+__global__ void __launch_bounds__(128)
+prox_reduce_kernel(const float* __restrict__ loss_rows, int B, int L, const int* __restrict__ n_res, float lamda,
+                   float inv_n_total, float* __restrict__ out) {
+  __shared__ float sh[2][128];
+  prox_reduce_item(loss_rows, blockIdx.x, B, L, n_res, lamda, inv_n_total, out, sh);
+}
+
+// mask = per_res > mean(per_res of the row's item), expanded to the 4 chi; z = SC_D * mask; x = z; m = v = 0
+// (optimize.py:5-31,47).  mean [items][2] (slot 1 = mean clash) or, with one_mean, a single pair for every row.
+__global__ void prox_init_kernel(const float* __restrict__ per_res, const float* __restrict__ mean, int one_mean,
+                                 const float* __restrict__ sc_d, int R, int B, int L, const unsigned char* __restrict__ owned,
+                                 unsigned char* __restrict__ mask, float* __restrict__ z, float* __restrict__ x,
+                                 float* __restrict__ m, float* __restrict__ v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R * 4) return;
-  bool mk = per_res[i >> 2] > mean[1] && (owned == nullptr || owned[i >> 2] != 0);
+  const int r = i >> 2;
+  const int it = one_mean ? 0 : r / L;  // = s * B + b
+  bool mk = per_res[r] > mean[(size_t)it * 2 + 1] && (owned == nullptr || owned[r] != 0);
   mask[i] = mk;
   float zz = mk ? sc_d[i] : 0.f * sc_d[i];
   z[i] = zz;
@@ -424,6 +490,8 @@ __global__ void prox_init_kernel(const float* __restrict__ per_res, const float*
 
 using namespace pp;
 
+static const ReduceArgs kNoReduce{nullptr, 0, 0, 0, nullptr, 0.f, 0.f, nullptr};
+
 extern "C" int pp_atom14_fwd(const float* tables, const float* X, const int64_t* residue_type, const float* chi,
                              int64_t G, int64_t S, float* xyz_out, cudaStream_t stream) {
   PP_REQUIRE(tables && X && residue_type && chi && xyz_out, "null pointer");
@@ -431,7 +499,7 @@ extern "C" int pp_atom14_fwd(const float* tables, const float* X, const int64_t*
   long long R = S * G;
   atom14_kernel<<<(unsigned)((R + 127) / 128), 128, 0, stream>>>(tables, X, (const long long*)residue_type, chi, nullptr,
                                                                 nullptr, (int)G, (int)S, xyz_out, nullptr, nullptr,
-                                                                nullptr, nullptr);
+                                                                nullptr, nullptr, kNoReduce);
   return check_launch("pp_atom14_fwd");
 }
 
@@ -477,46 +545,47 @@ extern "C" int pp_clash_fwd_bwd(const float* tables, const float* lower, const f
   long long R = S * G;
   atom14_kernel<<<(unsigned)((R + 127) / 128), 128, 0, stream>>>(tables, X, (const long long*)residue_type, chi, nullptr,
                                                                 nullptr, (int)G, (int)S, nullptr, atom_exists,
-                                                                (float4*)atoms4, axes, bound);
+                                                                (float4*)atoms4, axes, bound, kNoReduce);
   AdamArgs ad{};
   unsigned blocks = (unsigned)((R + 3) / 4);
   if (mode == 0)
     clash_pair_kernel<0><<<blocks, 128, 0, stream>>>((const float4*)atoms4, bound, axes, X, (const long long*)residue_type,
                                                      atom_exists, (const long long*)nbr_start, nbr_list, lower, upper,
-                                                     tables, nullptr, 0.f, tol, max_cut, (int)G, (int)S, per_res, nullptr,
-                                                     ad, nullptr);
+                                                     tables, nullptr, tol, max_cut, (int)G, (int)S, per_res, nullptr, ad);
   else
     clash_pair_kernel<1><<<blocks, 128, 0, stream>>>((const float4*)atoms4, bound, axes, X, (const long long*)residue_type,
                                                      atom_exists, (const long long*)nbr_start, nbr_list, lower, upper,
-                                                     tables, res_w, 0.f, tol, max_cut, (int)G, (int)S, per_res, grad_chi,
-                                                     ad, nullptr);
+                                                     tables, res_w, tol, max_cut, (int)G, (int)S, per_res, grad_chi, ad);
   return check_launch("pp_clash_fwd_bwd");
 }
 
-// Number of floats the proximal partial-sum workspace needs for R residue rows.
-extern "C" int64_t pp_prox_partial_floats(int64_t R) { return 2 * ((R + 3) / 4) + 8; }
+// ---- proximal_optimizer (optimize.py:5-73) for S samples of a padded batch of B complexes: items (s, b) are
+//      independent problems that share one launch; item (s, b) owns rows s*B*L + b*L + [0, n_res[b]).
 
-// Clash mask and optimiser state from the starting angles (optimize.py:5-31,47-51): one loss evaluation,
-// its mean, mask = per_res > mean, z = SC_D*mask, x = z, Adam moments zero.  mean_out[0:2] = {unused, mean}.
+// Clash mask and optimiser state from the starting angles (optimize.py:5-31,47-51): one loss evaluation, its mean
+// per item, mask = per_res > mean, z = SC_D*mask, x = z, Adam moments zero.  mean_out [S*B][2] = {unused, mean}.
 extern "C" int pp_prox_init(const float* tables, const float* lower, const float* upper, const float* X,
                             const int64_t* residue_type, const float* atom_exists, const int64_t* nbr_start,
-                            const int32_t* nbr_list, const float* sc_d, int64_t G, float tol, float max_cut,
-                            uint8_t* mask, float* z, float* x, float* m, float* v, float* per_res, float* mean_out,
-                            float* atoms4, float* axes, float* bound, float* partial, cudaStream_t stream) {
+                            const int32_t* nbr_list, const float* sc_d, int64_t B, int64_t L, int64_t S,
+                            const int32_t* n_res, float tol, float max_cut, uint8_t* mask, float* z, float* x, float* m,
+                            float* v, float* per_res, float* mean_out, float* atoms4, float* axes, float* bound,
+                            float* loss_rows, cudaStream_t stream) {
   PP_REQUIRE(tables && lower && upper && X && residue_type && atom_exists && nbr_start && nbr_list && sc_d, "null pointer");
-  PP_REQUIRE(mask && z && x && m && v && per_res && mean_out && atoms4 && axes && bound && partial, "null output");
-  PP_REQUIRE(G > 0, "bad sizes");
-  atom14_kernel<<<(unsigned)((G + 127) / 128), 128, 0, stream>>>(tables, X, (const long long*)residue_type, sc_d, nullptr,
-                                                                nullptr, (int)G, 1, nullptr, atom_exists, (float4*)atoms4,
-                                                                axes, bound);
+  PP_REQUIRE(mask && z && x && m && v && per_res && mean_out && atoms4 && axes && bound && loss_rows, "null output");
+  PP_REQUIRE(B > 0 && L > 0 && S > 0, "bad sizes");
+  const long long G = B * L, R = S * G;
+  atom14_kernel<<<(unsigned)((R + 127) / 128), 128, 0, stream>>>(tables, X, (const long long*)residue_type, sc_d, nullptr,
+                                                                nullptr, (int)G, (int)S, nullptr, atom_exists,
+                                                                (float4*)atoms4, axes, bound, kNoReduce);
   AdamArgs ad{};
-  unsigned blocks = (unsigned)((G + 3) / 4);
-  clash_pair_kernel<0><<<blocks, 128, 0, stream>>>((const float4*)atoms4, bound, axes, X, (const long long*)residue_type,
-                                                   atom_exists, (const long long*)nbr_start, nbr_list, lower, upper, tables,
-                                                   nullptr, 0.f, tol, max_cut, (int)G, 1, per_res, nullptr, ad, partial);
-  prox_reduce_kernel<<<1, 256, 0, stream>>>(partial, (int)blocks, 1.f, 1.f / (float)G, mean_out);
-  prox_init_kernel<<<(unsigned)((G * 4 + 255) / 256), 256, 0, stream>>>(per_res, mean_out, sc_d, (int)G, nullptr, mask, z, x,
-                                                                        m, v);
+  ad.L = (int)L;
+  ad.loss_rows = loss_rows;
+  clash_pair_kernel<0><<<(unsigned)((R + 3) / 4), 128, 0, stream>>>(
+      (const float4*)atoms4, bound, axes, X, (const long long*)residue_type, atom_exists, (const long long*)nbr_start,
+      nbr_list, lower, upper, tables, nullptr, tol, max_cut, (int)G, (int)S, per_res, nullptr, ad);
+  prox_reduce_kernel<<<(unsigned)(S * B), 128, 0, stream>>>(loss_rows, (int)B, (int)L, n_res, 1.f, 0.f, mean_out);
+  prox_init_kernel<<<(unsigned)((R * 4 + 255) / 256), 256, 0, stream>>>(per_res, mean_out, 0, sc_d, (int)R, (int)B, (int)L,
+                                                                        nullptr, mask, z, x, m, v);
   return check_launch("pp_prox_init");
 }
 
@@ -527,32 +596,46 @@ extern "C" int pp_prox_init_from_mean(const float* per_res, const float* mean, c
                                       cudaStream_t stream) {
   PP_REQUIRE(per_res && mean && sc_d && mask && z && x && m && v, "null pointer");
   PP_REQUIRE(G > 0, "bad sizes");
-  prox_init_kernel<<<(unsigned)((G * 4 + 255) / 256), 256, 0, stream>>>(per_res, mean, sc_d, (int)G, owned, mask, z, x, m, v);
+  prox_init_kernel<<<(unsigned)((G * 4 + 255) / 256), 256, 0, stream>>>(per_res, mean, 1, sc_d, (int)G, 1, (int)G, owned, mask,
+                                                                        z, x, m, v);
   return check_launch("pp_prox_init_from_mean");
 }
 
-// One proximal step (optimize.py:60-71): loss and gradient at the current x, Adam update, snapshot, loss value.
-//   loss_out[0] = loss BEFORE the update (what the reference appends to loss_list), loss_out[1] = mean clash.
+// One proximal step (optimize.py:60-71): loss and gradient at the current x, Adam update, snapshot.  Two launches:
+// the atom14 rebuild - whose tail blocks reduce the objective of the PREVIOUS step into prev_loss_out [S*B][2] when it
+// is non-null - and the pair kernel, which leaves this step's per-row terms in loss_rows.  pp_prox_loss reduces the
+// last step.  loss[it][0] = objective BEFORE the update (what the reference appends to loss_list), [1] = mean clash.
 extern "C" int pp_prox_step(const float* tables, const float* lower, const float* upper, const float* X,
                             const int64_t* residue_type, const float* atom_exists, const int64_t* nbr_start,
                             const int32_t* nbr_list, const float* sc_d, const uint8_t* mask, const float* z, float* x,
-                            float* m, float* v, int64_t G, float tol, float max_cut, float lamda, float step_size,
-                            float bc2_sqrt, float beta1, float beta2, float eps, float* snapshot, float* loss_out,
-                            float* per_res, float* atoms4, float* axes, float* bound, float* partial,
-                            const uint8_t* owned, int64_t n_total, cudaStream_t stream) {
+                            float* m, float* v, int64_t B, int64_t L, int64_t S, const int32_t* n_res, float tol,
+                            float max_cut, float lamda, float step_size, float bc2_sqrt, float beta1, float beta2,
+                            float eps, float* snapshot, float* prev_loss_out, float* per_res, float* atoms4, float* axes,
+                            float* bound, float* loss_rows, const uint8_t* owned, int64_t n_total, cudaStream_t stream) {
   PP_REQUIRE(tables && lower && upper && X && residue_type && atom_exists && nbr_start && nbr_list && sc_d, "null pointer");
-  PP_REQUIRE(mask && z && x && m && v && snapshot && loss_out && per_res && atoms4 && axes && bound && partial, "null output");
-  PP_REQUIRE(G > 0, "bad sizes");
-  atom14_kernel<<<(unsigned)((G + 127) / 128), 128, 0, stream>>>(tables, X, (const long long*)residue_type, x, sc_d, mask,
-                                                                (int)G, 1, nullptr, atom_exists, (float4*)atoms4, axes,
-                                                                bound);
-  const float inv_n = 1.f / (float)(n_total > 0 ? n_total : G);  // mean over the residues of the WHOLE complex
-  AdamArgs ad{x, m, v, z, sc_d, mask, snapshot, owned, step_size, bc2_sqrt, beta1, beta2, eps, inv_n};
-  unsigned blocks = (unsigned)((G + 3) / 4);
-  clash_pair_kernel<2><<<blocks, 128, 0, stream>>>((const float4*)atoms4, bound, axes, X, (const long long*)residue_type,
-                                                   atom_exists, (const long long*)nbr_start, nbr_list, lower, upper, tables,
-                                                   nullptr, lamda * inv_n, tol, max_cut, (int)G, 1, per_res, nullptr, ad,
-                                                   partial);
-  prox_reduce_kernel<<<1, 256, 0, stream>>>(partial, (int)blocks, lamda, inv_n, loss_out);
+  PP_REQUIRE(mask && z && x && m && v && snapshot && per_res && atoms4 && axes && bound && loss_rows, "null output");
+  PP_REQUIRE(B > 0 && L > 0 && S > 0, "bad sizes");
+  const long long G = B * L, R = S * G;
+  const float inv_n_total = n_total > 0 ? 1.f / (float)n_total : 0.f;  // slab: mean over the WHOLE complex
+  const unsigned nb = (unsigned)((R + 127) / 128);
+  ReduceArgs red{prev_loss_out ? loss_rows : nullptr, (int)nb, (int)B, (int)L, n_res, lamda, inv_n_total, prev_loss_out};
+  atom14_kernel<<<nb + (prev_loss_out ? (unsigned)(S * B) : 0u), 128, 0, stream>>>(
+      tables, X, (const long long*)residue_type, x, sc_d, mask, (int)G, (int)S, nullptr, atom_exists, (float4*)atoms4, axes,
+      bound, red);
+  AdamArgs ad{x, m, v, z, sc_d, mask, snapshot, owned, step_size, bc2_sqrt, beta1, beta2, eps, lamda, inv_n_total, n_res,
+              (int)L, loss_rows};
+  clash_pair_kernel<2><<<(unsigned)((R + 3) / 4), 128, 0, stream>>>(
+      (const float4*)atoms4, bound, axes, X, (const long long*)residue_type, atom_exists, (const long long*)nbr_start,
+      nbr_list, lower, upper, tables, nullptr, tol, max_cut, (int)G, (int)S, per_res, nullptr, ad);
   return check_launch("pp_prox_step");
+}
+
+// Objective of the step whose per-row terms are in loss_rows (the last step of a loop) -> loss_out [S*B][2].
+extern "C" int pp_prox_loss(const float* loss_rows, int64_t B, int64_t L, int64_t S, const int32_t* n_res, float lamda,
+                            int64_t n_total, float* loss_out, cudaStream_t stream) {
+  PP_REQUIRE(loss_rows && loss_out, "null pointer");
+  PP_REQUIRE(B > 0 && L > 0 && S > 0, "bad sizes");
+  prox_reduce_kernel<<<(unsigned)(S * B), 128, 0, stream>>>(loss_rows, (int)B, (int)L, n_res, lamda,
+                                                            n_total > 0 ? 1.f / (float)n_total : 0.f, loss_out);
+  return check_launch("pp_prox_loss");
 }

@@ -122,11 +122,6 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
-// instruction descriptor: D = fp32, A = B = tf32, both K-major, M x N tile
-__host__ __device__ constexpr uint32_t idesc_tf32(uint32_t M, uint32_t N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
-}
-
 // instruction descriptor: D = fp32, A = B = fp16 (format 0), both K-major, M x N tile; one instruction covers K = 16
 __host__ __device__ constexpr uint32_t idesc_f16(uint32_t M, uint32_t N) {
   return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
@@ -183,39 +178,10 @@ __device__ __forceinline__ void mma_f16_ts2(uint32_t d_tmem, uint32_t a_tmem, ui
       : "memory");
 }
 
-// D[tmem] (+)= A[smem] * B[smem]^T, one elected thread
-__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem]^T
-__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // all previously issued MMAs of this thread complete -> one arrival on the mbarrier
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
-}
-
-// fp32 -> (hi, lo) with hi = x truncated to TF32 (low 13 mantissa bits cleared, which is what the tensor core does to
-// its inputs anyway) and lo = x - hi, exact in fp32 and left unrounded: hi*B + lo*B carries 21+ bits of x.
-// Measured on B200 (30-step trajectories, tests/test_gpu_tc.py): with this split the per-edge GEMM chains end within
-// 1.9e-5 rad of the reference.
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-  lo = x - hi;
 }
 
 // Two fp32 values -> packed fp16 (hi, lo) pairs, x ~= hi + lo with both halves rounded to nearest: hi carries 11

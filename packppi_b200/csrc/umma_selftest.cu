@@ -1,5 +1,5 @@
-// Self-test of the tcgen05 primitives in umma.cuh: one 128 x 128 tile D = A W^T on the tensor cores, A either
-// staged in shared memory (SS) or written to TMEM (TS), 1 pass (plain TF32) or 3 passes (TF32 split, ~fp32).
+// Self-test of the tcgen05 primitives in umma.cuh: one 128 x 128 tile D = A W^T on the tensor cores (kind::f16), A
+// either staged in shared memory (SS) or written to TMEM (TS), 1 pass (plain fp16) or 3 passes (split fp16, ~fp32).
 // Used by tests/test_gpu_umma.py to pin the descriptor encodings before the fused kernels rely on them.
 #include "common.cuh"
 #include "umma.cuh"
@@ -9,111 +9,6 @@ namespace pp {
 using namespace umma;
 
 constexpr int kSelfKC = 32;  // k-columns per chunk
-constexpr uint32_t kSlotBytes = 128 * kSelfKC * 4;
-
-__global__ void __launch_bounds__(192, 1)
-umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ W, float* __restrict__ D, int K,
-                     int passes, int ts_mode) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  float* a_hi = reinterpret_cast<float*>(smem);
-  float* a_lo = reinterpret_cast<float*>(smem + kSlotBytes);
-  float* b_hi = reinterpret_cast<float*>(smem + 2 * kSlotBytes);
-  float* b_lo = reinterpret_cast<float*>(smem + 3 * kSlotBytes);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 4 * kSlotBytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 4 * kSlotBytes + 16);
-  const int tid = threadIdx.x, warp = tid >> 5;
-
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    mbar_fence_init();
-  }
-  if (warp == 4) tmem_alloc<512>(tmem_slot);
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t acc = tmem;             // columns [0,128)
-  const uint32_t a_t_hi = tmem + 128;    // columns [128,160) : A chunk (hi) when ts_mode
-  const uint32_t a_t_lo = tmem + 160;    // columns [160,192)
-  const uint32_t idesc = idesc_tf32(128, 128);
-  uint32_t phase = 0;
-
-  for (int k0 = 0; k0 < K; k0 += kSelfKC) {
-    if (tid < 128) {
-      const int row = tid;
-      const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-      uint32_t vh[32], vl[32];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        float4 x = *reinterpret_cast<const float4*>(A + (size_t)row * K + k0 + u * 4);
-        float4 h, l;
-        split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
-        if (ts_mode) {
-          vh[u * 4] = __float_as_uint(h.x); vh[u * 4 + 1] = __float_as_uint(h.y);
-          vh[u * 4 + 2] = __float_as_uint(h.z); vh[u * 4 + 3] = __float_as_uint(h.w);
-          vl[u * 4] = __float_as_uint(l.x); vl[u * 4 + 1] = __float_as_uint(l.y);
-          vl[u * 4 + 2] = __float_as_uint(l.z); vl[u * 4 + 3] = __float_as_uint(l.w);
-        } else {
-          int off = u * (128 * 4) + (row >> 3) * 32 + (row & 7) * 4;  // floats
-          *reinterpret_cast<float4*>(a_hi + off) = h;
-          *reinterpret_cast<float4*>(a_lo + off) = l;
-        }
-        float4 w = *reinterpret_cast<const float4*>(W + (size_t)row * K + k0 + u * 4);
-        split_tf32(w.x, h.x, l.x); split_tf32(w.y, h.y, l.y); split_tf32(w.z, h.z, l.z); split_tf32(w.w, h.w, l.w);
-        int off = u * (128 * 4) + (row >> 3) * 32 + (row & 7) * 4;
-        *reinterpret_cast<float4*>(b_hi + off) = h;
-        *reinterpret_cast<float4*>(b_lo + off) = l;
-      }
-      if (ts_mode) {
-        tmem_st32(a_t_hi + lane_base, vh);
-        tmem_st32(a_t_lo + lane_base, vl);
-        tmem_st_wait();
-      }
-      fence_async_smem();
-    }
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-    if (tid == 128) {
-      for (int p = 0; p < passes; ++p) {
-        // pass 0: hi*hi, pass 1: hi*lo, pass 2: lo*hi
-        const float* as = (p == 2) ? a_lo : a_hi;
-        const float* bs = (p == 1) ? b_lo : b_hi;
-        const uint32_t at = (p == 2) ? a_t_lo : a_t_hi;
-#pragma unroll
-        for (int kk = 0; kk < kSelfKC; kk += 8) {
-          uint64_t bd = smem_desc(smem_u32(bs) + (kk / 4) * 2048, 2048, 128);
-          uint32_t accum = (k0 > 0 || p > 0 || kk > 0) ? 1u : 0u;
-          if (ts_mode) {
-            mma_tf32_ts(acc, at + kk, bd, idesc, accum);
-          } else {
-            uint64_t ad = smem_desc(smem_u32(as) + (kk / 4) * 2048, 2048, 128);
-            mma_tf32_ss(acc, ad, bd, idesc, accum);
-          }
-        }
-      }
-      mma_commit(bar);
-    }
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    fence_after_sync();
-  }
-
-  if (tid < 128) {
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-#pragma unroll 1
-    for (int c = 0; c < 128; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(acc + lane_base + c, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) D[(size_t)tid * 128 + c + j] = __uint_as_float(v[j]);
-    }
-  }
-  fence_before_sync();
-  __syncthreads();
-  if (warp == 4) tmem_dealloc<512>(tmem);
-}
 
 // Same tile through kind::f16: fp16 (hi, lo) operand pairs, 16 k-columns per instruction, packed TMEM A operand.
 constexpr uint32_t kSlotBytes16 = 128 * kSelfKC * 2;
@@ -261,22 +156,7 @@ umma_selftest_f16_kernel(const float* __restrict__ A, const float* __restrict__ 
 
 }  // namespace pp
 
-// Diagnostics: D[128][128] = A[128][K] * W[128][K]^T on tcgen05 (K % 32 == 0).  passes: 1 = TF32, 3 = split TF32.
-extern "C" int pp_selftest_umma(const float* A, const float* W, float* D, int64_t K, int64_t passes, int64_t ts_mode,
-                                cudaStream_t stream) {
-  PP_REQUIRE(A && W && D, "null pointer");
-  PP_REQUIRE(K > 0 && K % 32 == 0, "K must be a positive multiple of 32");
-  PP_REQUIRE(passes == 1 || passes == 3, "passes must be 1 or 3");
-  size_t smem = 4 * pp::kSlotBytes + 64;
-  cudaError_t e = cudaFuncSetAttribute(pp::umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) {
-    snprintf(pp::g_last_error, sizeof(pp::g_last_error), "pp_selftest_umma: %s", cudaGetErrorString(e));
-    return 1;
-  }
-  pp::umma_selftest_kernel<<<1, 192, smem, stream>>>(A, W, D, (int)K, (int)passes, (int)ts_mode);
-  return pp::check_launch("pp_selftest_umma");
-}
-
+// Diagnostics: D[128][128] = A[128][K] * W[128][K]^T on tcgen05 (K % 32 == 0)
 // Same through kind::f16 with fp16 (hi, lo) pairs: passes 1 = plain fp16 inputs, 3 = split fp16 (~fp32).
 extern "C" int pp_selftest_umma_f16(const float* A, const float* W, float* D, int64_t K, int64_t passes,
                                     int64_t ts_mode, cudaStream_t stream) {

@@ -58,6 +58,8 @@ class Graph:
     """Step-invariant state of one padded batch: neighbour lists, geometry records,
     attention mask and, once `edge_embed` ran, the embedded edge features h_E0."""
 
+    ni = step_mask = mask_1pi = None  # filled by Engine.build_graph
+
     def __init__(self, X, residue_mask, top_k=TOP_K):
         dev = X.device
         self.B, self.L = int(X.shape[0]), int(X.shape[1])
@@ -110,18 +112,41 @@ class Graph:
 
 
 class Workspace:
-    """Per-sample activations and scratch for S*G residue rows."""
+    """Per-sample activations and scratch for S*G residue rows: views into the capacity buffers of a `WorkspacePool`
+    (or freshly allocated when no pool is given, e.g. for a captured CUDA graph that must own its memory)."""
 
-    def __init__(self, G, K, S, dev):
+    def __init__(self, G, K, S, dev, pool=None):
         R = S * G
-        z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)  # noqa: E731
         self.G, self.K, self.S = G, K, S
-        self.hV = z(R, 128)
-        self.hE = z(R, K, 128)
-        self.wsA, self.wsN, self.wsAcc = z(R, 128), z(R, 128), z(R, 128)
-        self.wsP = z(R, 24)
-        self.score = z(R, 4)
+        if pool is None:
+            z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)  # noqa: E731
+            self.hV, self.hE = z(R, 128), z(R, K, 128)
+            self.wsA, self.wsN, self.wsAcc = z(R, 128), z(R, 128), z(R, 128)
+            self.wsP, self.score = z(R, 24), z(R, 4)
+        else:
+            v = lambda name, *shape: pool.view(name, shape)  # noqa: E731
+            self.hV, self.hE = v("hV", R, 128), v("hE", R, K, 128)
+            self.wsA, self.wsN, self.wsAcc = v("wsA", R, 128), v("wsN", R, 128), v("wsAcc", R, 128)
+            self.wsP, self.score = v("wsP", R, 24), v("score", R, 4)
         self.clean_for = None  # Graph.serial whose padding rows of hE / wsAcc are known to be zero
+
+
+class WorkspacePool:
+    """One set of flat buffers per engine, grown to the largest micro-batch seen and then reused for every shape
+    (a sweep of ragged micro-batches used to free and re-allocate 1-2 GB whenever the padded shape changed)."""
+
+    def __init__(self, dev):
+        self.dev, self.buf = dev, {}
+
+    def view(self, name, shape):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        cur = self.buf.get(name)
+        if cur is None or cur.numel() < n:
+            self.buf[name] = None  # release the old block before the larger one is requested
+            cur = self.buf[name] = torch.zeros(n, dtype=torch.float32, device=self.dev)
+        return cur[:n].view(*shape)
 
 
 class Engine:
@@ -134,22 +159,23 @@ class Engine:
     #   f16    tensor cores, hi halves only (11 mantissa bits, the precision of TF32): fast mode, looser stated tolerance
     # node_epilogue: where the per-residue node update (W_out, LayerNorm, FFN 128-512-128, LayerNorm) runs:
     #   "tc32" tensor cores with promoted accumulation (csrc/node_post_tc.cu; default of the tensor-core modes)
-    #   "ffma" exact-fp32 CUDA-core kernel            "tc" tensor cores, plain TMEM accumulation
+    #   "ffma" exact-fp32 CUDA-core kernel
     # The tensor core accumulates in fp32 with truncation (measured bias -7e-7 relative at K = 128, growing linearly
-    # with K), which the h_V path amplifies: against the CPU oracle on fresh inputs (tests/diag_accuracy.py) the max
-    # chi error after 2 / 30 steps is 1.2e-4 / 3.0e-5 rad with "tc" (gate: 1e-4 at every step), 4.7e-5 / 9.2e-6 with
-    # "ffma" and 4.5e-5 / 8.3e-6 with "tc32" (fp32 mode: 5.1e-5 / 6.7e-6); throughput 5.93 / 5.30 / 5.81 M.  The
-    # residue prologue (points, A_i, N_j) is accuracy-neutral and always runs on the tensor cores in these modes.
+    # with K), which the h_V path amplifies (1.2e-4 rad after two ODE steps with plain TMEM accumulation, over the 1e-4
+    # gate; that variant was removed).  Against the CPU oracle on fresh inputs (tests/diag_accuracy.py, 64 complexes)
+    # the max chi error after 2 / 30 steps is 6.5e-5 / 9.5e-6 rad with "ffma" and 5.7e-5 / 1.05e-5 with "tc32" (fp32
+    # mode: 4.4e-5 / 7.6e-6).  The residue prologue (points, A_i, N_j) is accuracy-neutral and always runs on the tensor
+    # cores in these modes.
     MODES = ("fp32", "f16x3", "f16")
     _serial = 0
-    ALIASES = {"tf32x3": "f16x3", "tf32": "f16"}   # names of the first tensor-core implementation (split TF32)
 
     def __init__(self, state_dict, device, mode="f16x3", cluster=1, node_epilogue=None):
-        mode = self.ALIASES.get(mode, mode)
         if node_epilogue is None:
             node_epilogue = "tc32"
-        if node_epilogue not in ("tc", "tc32", "ffma"):
-            raise ValueError("node_epilogue must be 'tc32', 'tc' or 'ffma'")
+        if node_epilogue not in ("tc32", "ffma"):
+            raise ValueError("node_epilogue must be 'tc32' or 'ffma'")
+        if int(cluster) not in (1, 2):
+            raise ValueError("cluster must be 1 or 2")
         self.node_epilogue = node_epilogue
         if mode not in self.MODES:
             raise ValueError(f"mode must be one of {self.MODES}")
@@ -167,6 +193,7 @@ class Engine:
         self.wpre = pack_pre_stream(state_dict, _lib.load().pp_tc_pre_stream_floats()).to(self.dev)
         self.tables = DeviceTables.get(self.dev)
         self._ws = {}
+        self._pool = WorkspacePool(self.dev)
         self._sched = {}
 
     # ------------------------------------------------------------------ graph
@@ -181,13 +208,20 @@ class Engine:
             g = Graph(X, mask)
         if with_edges:
             g.edge_embed(self.wblob, batch.residue_index, batch.chain_indices)
+        # per-batch constants of the sampling loop, built once per graph instead of once per sampling call
+        g.ni = self.node_inputs(batch)
+        m1 = batch.chi_1pi_periodic_mask.to(self.dev).reshape(-1, 4).bool()
+        g.step_mask = (m1 | batch.chi_2pi_periodic_mask.to(self.dev).reshape(-1, 4).bool()).to(torch.uint8).contiguous()
+        g.mask_1pi = m1.to(torch.uint8).contiguous()
         return g
 
     def workspace(self, G, K, S):
+        """Activations for S*G rows: views into this engine's capacity buffers (one live shape at a time: asking for
+        another shape re-labels the same memory, so its padding rows count as dirty again)."""
         key = (G, K, S)
         if key not in self._ws:
-            self._ws.clear()  # one live shape at a time keeps memory bounded
-            self._ws[key] = Workspace(G, K, S, self.dev)
+            self._ws.clear()
+            self._ws[key] = Workspace(G, K, S, self.dev, pool=self._pool)
         return self._ws[key]
 
     # ------------------------------------------------------------------ network
@@ -234,13 +268,9 @@ class Engine:
                           ws.wsN, ws.wsP, ws.wsAcc, *tcp, rows=S * G, tag="node")
             if self.mode == "fp32" or self.node_epilogue == "ffma":
                 _lib.call("pp_ipmp_node_post", W, layer, *common, graph.msum, *size, ws.wsAcc, ws.hV, rows=S * G)
-            elif self.node_epilogue == "tc32":
+            else:
                 _lib.call("pp_ipmp_node_post_tc32", W, layer, self.wtc[layer, 2], graph.msum, graph.mask, G, K, S,
                           ws.wsAcc, ws.hV, rows=S * G)
-            else:
-                # plain TMEM accumulation; always the 3-pass split, also in the fast mode
-                _lib.call("pp_ipmp_node_post_tc", W, layer, self.wtc[layer, 2], graph.msum, graph.mask, G, K, S,
-                          ws.wsAcc, ws.hV, 3, self.cluster, rows=S * G)
             if edge:
                 pre(1)
                 if self.mode == "fp32":
@@ -255,7 +285,7 @@ class Engine:
         """chi [S*G,4] (device), t [S*G] -> (score [S*G,4], h_V [S*G,128])  (TorsionalDiffusion.py:90-109)."""
         S = chi.shape[0] // graph.G
         ws = self.workspace(graph.G, graph.K, S)
-        ni = self.node_inputs(batch)
+        ni = graph.ni if getattr(graph, "ni", None) is not None else self.node_inputs(batch)
         self.forward_layers(graph, ws, ni, chi, t, 1)
         _lib.call("pp_decode_step", self.wblob, ws.hV, graph.G, S, ws.score, 0, 0.0, 0.0, None, None, None, None, None,
                   None, 0.0)
@@ -314,9 +344,12 @@ class Engine:
         captured CUDA graph of the whole loop from the second call on."""
         G, K = graph.G, graph.K
         S = chi_init.shape[0] // G
-        ni = self.node_inputs(batch)
-        step_mask = (batch.chi_1pi_periodic_mask.to(self.dev).reshape(-1, 4).bool() |
-                     batch.chi_2pi_periodic_mask.to(self.dev).reshape(-1, 4).bool()).to(torch.uint8).contiguous()
+        if getattr(graph, "ni", None) is not None:
+            ni, step_mask = graph.ni, graph.step_mask
+        else:  # a Graph built outside build_graph
+            ni = self.node_inputs(batch)
+            step_mask = (batch.chi_1pi_periodic_mask.to(self.dev).reshape(-1, 4).bool() |
+                         batch.chi_2pi_periodic_mask.to(self.dev).reshape(-1, 4).bool()).to(torch.uint8).contiguous()
         coefs, tvals = self._schedule(n_steps, annealed_temp, mode)
         if mode == "sde":  # fresh noise every step: no graph replay; `sde_noise` [steps, 2, S*G, 4] injects the draws
             if sde_noise is None:
@@ -420,45 +453,64 @@ class ClashContext:
                   per_res, grad, ws["atoms4"], ws["axes"], ws["bound"])
         return per_res, grad
 
-    def _prox_run(self, st, lamda, num_steps, lr, beta1, beta2, eps):
-        G = self.G
-        ws = self.scratch(1)
+    def n_res(self):
+        """int32 [B]: residues of every complex without the padding (index of the last residue that has an atom + 1);
+        the reference's means run over exactly these rows (it never sees a padded batch, optimize.py:27)."""
+        if self.B == 1:
+            return None  # one unpadded complex: every row counts, as in the reference
+        if getattr(self, "_n_res", None) is None:
+            has = self.exists.reshape(self.B, self.L, 14).sum(-1) > 0
+            idx = torch.arange(1, self.L + 1, device=self.dev).unsqueeze(0)
+            self._n_res = (has * idx).amax(1).clamp(min=1).to(torch.int32).contiguous()
+        return self._n_res
+
+    def _prox_run(self, st, S, lamda, num_steps, lr, beta1, beta2, eps):
+        B, L = self.B, self.L
+        ws = self.scratch(S)
+        n_res = self.n_res()
         static = (self.tables.geo, self.lower, self.upper, self.X, self.rtype, self.exists, self.start, self.list,
                   st["sc_d"])
-        _lib.call("pp_prox_init", *static, G, self.tol, self.max_cut, st["mask"], st["z"], st["x"], st["m"], st["v"],
-                  st["per_res"], st["mean"], ws["atoms4"], ws["axes"], ws["bound"], st["partial"])
+        _lib.call("pp_prox_init", *static, B, L, S, n_res, self.tol, self.max_cut, st["mask"], st["z"], st["x"], st["m"],
+                  st["v"], st["per_res"], st["mean"], ws["atoms4"], ws["axes"], ws["bound"], st["loss_rows"])
         for k in range(num_steps):
             t = k + 1
             step_size = lr / (1 - beta1 ** t)  # torch.optim.Adam, single-tensor path
             bc2_sqrt = math.sqrt(1 - beta2 ** t)
-            _lib.call("pp_prox_step", *static, st["mask"], st["z"], st["x"], st["m"], st["v"], G, self.tol,
+            _lib.call("pp_prox_step", *static, st["mask"], st["z"], st["x"], st["m"], st["v"], B, L, S, n_res, self.tol,
                       self.max_cut, float(lamda), step_size, bc2_sqrt, beta1, beta2, eps, st["snaps"][k],
-                      st["losses"][k], st["per_res"], ws["atoms4"], ws["axes"], ws["bound"], st["partial"], None, 0)
+                      st["losses"][k - 1] if k else None, st["per_res"], ws["atoms4"], ws["axes"], ws["bound"],
+                      st["loss_rows"], None, 0)
+        _lib.call("pp_prox_loss", st["loss_rows"], B, L, S, n_res, float(lamda), 0, st["losses"][num_steps - 1])
 
     def proximal(self, sc_d, lamda, num_steps, lr=1e-2, beta1=0.9, beta2=0.999, eps=1e-8):
-        """optimize.py:21-73 for one complex.  Returns (snapshots [num_steps,G,4], losses [num_steps], mask [G,4]);
-        everything stays on the device, the caller decides when to synchronise.  The 1 + 3*num_steps launches are
-        captured in a CUDA graph the second time the same context runs the same schedule."""
-        assert self.B == 1
+        """optimize.py:21-73 for every (sample, complex) item of the padded batch at once: sc_d [S*G, 4].
+        Returns (snapshots [num_steps, S*G, 4], losses [num_steps, S*B], mask [S*G, 4]); everything stays on the
+        device, the caller decides when to synchronise.  The 5 + 2*num_steps launches are captured in a CUDA graph
+        the second time the same context runs the same schedule."""
         G, dev = self.G, self.dev
-        key = (int(num_steps), float(lamda), lr, beta1, beta2, eps)
+        sc_d = sc_d.reshape(-1, 4)
+        S = sc_d.shape[0] // G
+        if S * G != sc_d.shape[0]:
+            raise RuntimeError("proximal: SC_D does not match the batch")
+        R, items = S * G, S * self.B
+        key = (S, int(num_steps), float(lamda), lr, beta1, beta2, eps)
         st = self._prox.get(key)
         if st is None:
             f = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)  # noqa: E731
-            st = dict(sc_d=f(G, 4), mask=torch.zeros(G, 4, dtype=torch.uint8, device=dev), z=f(G, 4), x=f(G, 4),
-                      m=f(G, 4), v=f(G, 4), per_res=f(G), mean=f(2), snaps=f(num_steps, G, 4), losses=f(num_steps, 2),
-                      partial=f(int(_lib.load().pp_prox_partial_floats(G))), calls=0, graph=None)
+            st = dict(sc_d=f(R, 4), mask=torch.zeros(R, 4, dtype=torch.uint8, device=dev), z=f(R, 4), x=f(R, 4),
+                      m=f(R, 4), v=f(R, 4), per_res=f(R), mean=f(items, 2), snaps=f(num_steps, R, 4),
+                      losses=f(num_steps, items, 2), loss_rows=f(R, 2), calls=0, graph=None)
             self._prox = {key: st}  # one schedule at a time keeps the memory bounded
-        st["sc_d"].copy_(sc_d.reshape(G, 4))
+        st["sc_d"].copy_(sc_d)
         st["calls"] += 1
         if st["calls"] == 1 or GRAPH_ROWS_MAX <= 0:
-            self._prox_run(st, lamda, num_steps, lr, beta1, beta2, eps)
+            self._prox_run(st, S, lamda, num_steps, lr, beta1, beta2, eps)
         else:
             if st["graph"] is None:
                 torch.cuda.synchronize(dev)
                 cg = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(cg):
-                    self._prox_run(st, lamda, num_steps, lr, beta1, beta2, eps)
+                    self._prox_run(st, S, lamda, num_steps, lr, beta1, beta2, eps)
                 st["graph"] = cg
             st["graph"].replay()
-        return st["snaps"].clone(), st["losses"][:, 0].clone(), st["mask"].clone()
+        return st["snaps"].clone(), st["losses"][:, :, 0].clone(), st["mask"].clone()

@@ -86,7 +86,7 @@ class _PackedModule(nn.Module):
     `kernel_mode` selects how the per-edge message MLPs run (engine.Engine.MODES): "fp32" = CUDA-core FFMA (exact),
     "f16x3" = tcgen05 tensor cores with split fp16 operand pairs (fp32-grade, default), "f16" = tensor cores, plain
     fp16 inputs (fast, looser tolerance).  `kernel_cluster` = CTAs per cluster sharing the weight stream in the
-    tensor-core modes (1, 2, 4).  `kernel_node_epilogue` = "tc32" (default) | "ffma" | "tc": where the per-residue node update runs.
+    tensor-core modes (1 or 2).  `kernel_node_epilogue` = "tc32" (default) | "ffma": where the per-residue node update runs.
     Defaults come from the environment (PACKPPI_B200_MODE, PACKPPI_B200_CLUSTER, PACKPPI_B200_NODE_EPILOGUE)."""
     kernel_mode = os.environ.get("PACKPPI_B200_MODE", "f16x3")
     kernel_cluster = int(os.environ.get("PACKPPI_B200_CLUSTER", "1"))
@@ -240,7 +240,8 @@ class TDiffusionModule(_PackedModule):
         data pointers: both are recycled as soon as a batch is freed, and a recycled key once served the graph of a
         5-residue complex to a 17-residue one."""
         eng = self.engine(batch.X.device)
-        tensors = (batch.X, batch.residue_mask, batch.residue_index, batch.chain_indices)
+        tensors = (batch.X, batch.residue_mask, batch.residue_index, batch.chain_indices, batch.residue_type,
+                   batch.BB_D_sincos, batch.SC_D_mask, batch.chi_1pi_periodic_mask, batch.chi_2pi_periodic_mask)
         key = (tensors, tuple(t._version for t in tensors), getattr(self, "_engine_sig", None))
         old = self._graph_cache[0]
         same = (old is not None and old[2] == key[2] and old[1] == key[1]
@@ -260,26 +261,80 @@ class TDiffusionModule(_PackedModule):
         eng, g = self._graph(batch)
         B, L = g.B, g.L
         chi = SC_D_noised.reshape(-1, 4).to(torch.float32).contiguous()
-        score, hV = eng.network(g, batch, chi, t.reshape(-1).to(device=chi.device, dtype=torch.float32).contiguous())
+        if chi.shape[0] == 0 or chi.shape[0] % (B * L) != 0:
+            raise ValueError(f"network: SC_D_noised has {chi.shape[0]} rows, not a multiple of B*L = {B * L}")
         lead = chi.shape[0] // (B * L)
+        t = t.reshape(-1).to(device=chi.device, dtype=torch.float32)
+        if t.numel() == B * L and lead > 1:
+            t = t.repeat(lead)  # one time per residue, shared by the samples
+        elif t.numel() != chi.shape[0]:
+            raise ValueError(f"network: t has {t.numel()} entries; expected B*L = {B * L} or S*B*L = {chi.shape[0]}")
+        score, hV = eng.network(g, batch, chi, t.contiguous())
         shape = (B, L) if lead == 1 else (lead, B, L)
         return score.reshape(*shape, 4).clone(), hV.reshape(*shape, H).clone()
 
+    @staticmethod
+    def _wrapped_normal_score(noise, sigma, PI):
+        """SO2Schedule.score (schedule.py:64-73): the reference looks the score of the wrapped normal up in a
+        5001 x 5001 table over log-spaced (x, sigma) grids (schedule.py:39-54, 200 MB per schedule, 20 s to build).
+        Here the table ENTRY the reference would read - same index rounding, same 201-image sums of `p` and `grad`
+        (schedule.py:10-22) in float64 - is evaluated on the fly for the values that are needed."""
+        X_MIN, X_N, S_MIN, S_MAX, S_N, N = 1e-5, 5000, 3e-3, 2.0, 5000, 100
+        # the index arithmetic runs in fp32 like the reference's (numpy on the fp32 arrays it is handed)
+        x = (noise.float() + PI) % (2 * PI) - PI
+        sign = torch.sign(x).double()
+        xi = torch.round(torch.clip((torch.log(x.abs() / PI + 1e-10) - np.log(X_MIN)) / (0 - np.log(X_MIN)) * X_N, 0, X_N))
+        si = torch.round(torch.clip((torch.log(sigma.float() / PI) - np.log(S_MIN)) / (np.log(S_MAX) - np.log(S_MIN)) * S_N,
+                                    0, S_N))
+        xi, si = xi.double(), si.double()
+        xg = 10 ** (np.log10(X_MIN) + xi * ((0 - np.log10(X_MIN)) / X_N)) * PI          # SO2Schedule.x[xi]
+        sg = 10 ** (np.log10(S_MIN) + si * ((np.log10(S_MAX) - np.log10(S_MIN)) / S_N)) * PI  # SO2Schedule.sigma[si]
+        xg = torch.where(xi == X_N, torch.full_like(xg, PI), xg)      # np.linspace ends exactly on its stop value
+        sg = torch.where(si == S_N, torch.full_like(sg, S_MAX * PI), sg)
+        k = torch.arange(-N, N + 1, device=x.device, dtype=torch.float64)
+        y = xg.unsqueeze(-1) + 2 * PI * k
+        sg = sg.expand_as(xg).unsqueeze(-1)
+        e = torch.exp(-y ** 2 / 2 / sg ** 2)
+        p, g = e.sum(-1), (y / sg ** 2 * e).sum(-1)
+        return (-sign * (g / torch.where(p == 0, torch.full_like(p, 1e-10), p))).to(noise.dtype)
+
     @torch.no_grad()
     def add_sc_noise(self, batch, t, noise=None, generator=None):
-        """TorsionalDiffusion.py:111-124 / schedule.py:176-196.  `noise` = (eps_1pi, eps_2pi), each [B*L,4] standard
-        normal, injects the two randn draws.  The second return value (the training-time score target, a host
-        table lookup in the reference, unused by `sampling`) is returned as zeros."""
+        """TorsionalDiffusion.py:111-124 / schedule.py:176-196 -> (noised angles, score target), both [B, L, 4].
+        `noise` = (eps_1pi, eps_2pi), each [B*L,4] standard normal, injects the two randn draws.  The score target
+        (training only; `sampling` drops it) is the reference's table value, evaluated instead of looked up."""
         x = batch.SC_D.reshape(-1, 4)
         dev = x.device
         sigma = torch.exp(np.log(SIGMA_MIN) + (np.log(SIGMA_MAX) - np.log(SIGMA_MIN)) * t.to(dev)).unsqueeze(-1)
         if noise is None:
             noise = (torch.randn(x.shape, device=dev, dtype=x.dtype, generator=generator),
                      torch.randn(x.shape, device=dev, dtype=x.dtype, generator=generator))
-        x = x + (noise[0].to(dev).reshape(-1, 4) * sigma) * batch.chi_1pi_periodic_mask.reshape(-1, 4)
-        x = x + (noise[1].to(dev).reshape(-1, 4) * sigma) * batch.chi_2pi_periodic_mask.reshape(-1, 4)
+        m1, m2 = batch.chi_1pi_periodic_mask.reshape(-1, 4), batch.chi_2pi_periodic_mask.reshape(-1, 4)
+        n1, n2 = noise[0].to(dev).reshape(-1, 4) * sigma, noise[1].to(dev).reshape(-1, 4) * sigma
+        score = torch.where(m1, self._wrapped_normal_score(n1, sigma, 0.5 * np.pi) * m1,
+                            self._wrapped_normal_score(n2, sigma, np.pi) * m2)
+        x = x + n1 * m1
+        x = x + n2 * m2
         x = (x + np.pi) % (2 * np.pi) - np.pi
-        return x.reshape(batch.num_proteins, -1, 4), torch.zeros_like(x).reshape(batch.num_proteins, -1, 4)
+        return x.reshape(batch.num_proteins, -1, 4), score.reshape(batch.num_proteins, -1, 4)
+
+    @torch.no_grad()
+    def _initial_samples(self, batch, S, noise, generator):
+        """add_sc_noise at t = 1 for S decoys in one shot: [S, B, L, 4].  noise = (eps_1pi, eps_2pi), each [S, B*L, 4]."""
+        x = batch.SC_D.reshape(1, -1, 4)
+        dev = x.device
+        # t_to_sigma(t = 1) with the fp32 tensor arithmetic of add_sc_noise (schedule.py:165-174)
+        sigma = torch.exp(np.log(SIGMA_MIN) + (np.log(SIGMA_MAX) - np.log(SIGMA_MIN)) * torch.ones(1, device=dev))
+        if noise is None:
+            shape = (S, x.shape[1], 4)
+            noise = (torch.randn(shape, device=dev, dtype=x.dtype, generator=generator),
+                     torch.randn(shape, device=dev, dtype=x.dtype, generator=generator))
+        n1 = noise[0].to(dev).reshape(S, -1, 4)
+        n2 = noise[1].to(dev).reshape(S, -1, 4)
+        x = x + (n1 * sigma) * batch.chi_1pi_periodic_mask.reshape(1, -1, 4)
+        x = x + (n2 * sigma) * batch.chi_2pi_periodic_mask.reshape(1, -1, 4)
+        x = (x + np.pi) % (2 * np.pi) - np.pi
+        return x.reshape(S, batch.num_proteins, -1, 4)
 
     def forward(self, batch):
         raise NotImplementedError("training (score-matching loss) is outside the hot path this package replaces; "
@@ -288,7 +343,9 @@ class TDiffusionModule(_PackedModule):
     def sampling(self, batch, use_proximal=False, return_list=False, init_SC_D=None, noise=None, n_samples=None,
                  generator=None, sde_noise=None):
         """TorsionalDiffusion.py:254-298.  Returns SC_D_sample [B,L,4]; with use_proximal the accepted proximal
-        result; with return_list (SC_D_sample, list of 50 [1,L,4] tensors, list of 50 floats).
+        result; with return_list (SC_D_sample, list of 50 [1,L,4] tensors, list of 50 floats).  With B > 1 or
+        n_samples the proximal stage runs all (sample, complex) items in one batch (components.proximal_optimizer) and
+        the accept rule is applied per item.
 
         n_samples = S draws S decoys that share graph and edge embedding and returns [S,B,L,4]
         (init_SC_D / noise then carry a leading S).  With sample_cfg.mode = "sde" (schedule.py:224-228) every step adds
@@ -298,12 +355,8 @@ class TDiffusionModule(_PackedModule):
         S = 1 if n_samples is None else int(n_samples)
         dev = batch.X.device
         if init_SC_D is None:
-            t1 = torch.ones(B * L, device=dev)
-            inits = []
-            for s in range(S):
-                ns = None if noise is None else ((noise[0][s], noise[1][s]) if n_samples is not None else noise)
-                inits.append(self.add_sc_noise(batch, t1, noise=ns, generator=generator)[0])
-            init_SC_D = torch.stack(inits)
+            init_SC_D = self._initial_samples(batch, S, noise if n_samples is not None or noise is None
+                                              else (noise[0][None], noise[1][None]), generator)
         chi0 = init_SC_D.to(device=dev, dtype=torch.float32).reshape(S * B * L, 4).contiguous()
         smp = self.hparams.sample_cfg
         if smp.mode not in ("ode", "sde"):
@@ -313,15 +366,17 @@ class TDiffusionModule(_PackedModule):
         SC_D_sample = chi.reshape(S, B, L, 4) if n_samples is not None else chi.reshape(B, L, 4)
         if not use_proximal:
             return SC_D_sample
-        if n_samples is not None:
-            raise NotImplementedError("use_proximal with n_samples: run proximal_optimizer per decoy")
         SC_D_resample_list, loss_list = proximal_optimizer(batch, SC_D_sample, smp.violation_tolerance_factor,
                                                            smp.clash_overlap_tolerance, smp.lamda, smp.num_steps)
         if return_list:
             return SC_D_sample, SC_D_resample_list, loss_list
-        if loss_list[-1] < loss_list[0]:
-            return SC_D_resample_list[-1]
-        return SC_D_sample
+        if not torch.is_tensor(loss_list[0]):  # one complex, one sample: the reference's accept rule (:295-298)
+            if loss_list[-1] < loss_list[0]:
+                return SC_D_resample_list[-1]
+            return SC_D_sample
+        # batched (B > 1 and / or n_samples): the same accept rule per (sample, complex) item
+        better = (loss_list[-1] < loss_list[0])[..., None, None]
+        return torch.where(better, SC_D_resample_list[-1], SC_D_sample)
 
     def compute_rmsd(self, true_coords, pred_coords, atom_mask, residue_mask):
         """TorsionalDiffusion.py:300-309 (mean squared deviation; the reference never takes the root)."""

@@ -23,16 +23,25 @@ def partition(lengths, world):
     return out
 
 
-def gather_angles(local, lengths, plan, n_samples):
+def _collective_device():
+    """Where collective buffers must live: the current CUDA device under NCCL, the host under gloo."""
+    if dist.is_initialized() and dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def gather_angles(local, lengths, plan, n_samples, device=None):
     """local: {complex index: tensor [S, L_c, 4]} of this rank -> list over ALL complexes of [S, L_c, 4] tensors,
-    identical on every rank.  One all_gather of a flat, equally padded buffer per rank."""
+    identical on every rank.  One all_gather of a flat, equally padded buffer per rank.  A rank may own nothing
+    (more ranks than complexes): its buffer then lives on `device` (default: the backend's device), not on
+    whatever its empty result list would suggest."""
     world = dist.get_world_size() if dist.is_initialized() else 1
     if world == 1:
         return [local[i] for i in range(len(lengths))]
     sizes = [sum(int(lengths[i]) for i in plan[r]) * n_samples * 4 for r in range(world)]
-    cap = max(sizes)
+    cap = max(max(sizes), 1)
     some = next(iter(local.values())) if local else None
-    dev = some.device if some is not None else torch.device("cpu")
+    dev = torch.device(device) if device is not None else (some.device if some is not None else _collective_device())
     rank = dist.get_rank()
     flat = torch.zeros(cap, dtype=torch.float32, device=dev)
     if local:
@@ -128,13 +137,18 @@ class SlabProximal:
     Every rank owns one slab of residues, keeps copies of the halo residues it interacts with, evaluates loss and
     gradient of its owned residues with the same kernels as the single-GPU path (every cross-boundary pair is
     evaluated on both sides, so no force has to travel back), and updates their angles.  Per step the ranks exchange
-    only the current angles of the owned residues (one all_gather, 16 B per residue); the loss values are summed
-    once at the end.  All ranks hold the full input batch (replicated); outputs are identical on every rank."""
+    only the current angles of the owned residues (one `all_gather_into_tensor` of equally padded buffers, 16 B per
+    residue); the loss values are summed once at the end.  All ranks hold the full input batch (replicated); outputs
+    are identical on every rank.
+
+    Everything per step is stream-ordered device work with pre-allocated buffers - two kernels, one packing gather,
+    the NCCL all-gather, one halo scatter - so the whole `num_steps` loop is captured in ONE CUDA graph (NCCL included)
+    on the second call with the same schedule and replayed from then on.  The halo is found on the GPU from the
+    clash neighbour list of the whole complex (`clash_nbr_cells_kernel`), not by a host-side tree search."""
 
     def __init__(self, batch, violation_tolerance_factor=12.0, clash_overlap_tolerance=0.5):
         import numpy as np
 
-        from . import tables
         from .engine import ClashContext
         assert batch.num_proteins == 1
         self.world = dist.get_world_size() if dist.is_initialized() else 1
@@ -144,59 +158,101 @@ class SlabProximal:
         self.L, self.dev = L, dev
         ca = batch.X[0, :, 1, :].detach().cpu().numpy()
         has_atoms = (batch.atom_mask[0].sum(-1) > 0).cpu().numpy()
-        rtype = batch.residue_type[0].cpu().numpy()
-        bb = (batch.X[0, :, :4, :] - batch.X[0, :, 1:2, :]).norm(dim=-1).max(-1)[0].cpu().numpy()
-        reach = np.maximum(tables.max_reach()[np.clip(rtype, 0, 20)], bb + 1e-3).astype(np.float64)
-        reach[~has_atoms] = -1.0
-        cutoff = max(2.0 * float(tables.raw()["clash_radius"].max()) - float(clash_overlap_tolerance), 0.0)
         self.owner = slab_partition(ca, has_atoms, self.world)
-        self.local = halo_of(ca, reach, self.owner, self.rank, cutoff)
-        self.counts = [int((self.owner == r).sum()) for r in range(self.world)]
-        self.ids_of = [torch.from_numpy(np.nonzero(self.owner == r)[0]).to(dev) for r in range(self.world)]
-        loc = torch.from_numpy(self.local).to(dev)
+        owner = torch.from_numpy(self.owner).to(dev)
+        mine = owner == self.rank
+        if self.world > 1:
+            # halo = residues of other ranks on the neighbour list of an owned residue (the list's own criterion:
+            # CA distance < reach_i + reach_j + cutoff), read off the whole complex's list on the device
+            whole = ClashContext(dev, batch.X, batch.residue_type, batch.atom_mask, batch.residue_index,
+                                 violation_tolerance_factor, clash_overlap_tolerance)
+            counts = (whole.start[1:] - whole.start[:-1])
+            row_of = torch.repeat_interleave(torch.arange(L, device=dev), counts)
+            nb = whole.list[:int(whole.start[-1].item())].long()
+            sel = mine[row_of] & ~mine[nb]
+            keep = mine.clone()
+            keep[nb[sel]] = True
+            del whole
+        else:
+            keep = mine
+        loc = torch.nonzero(keep)[:, 0]                      # ascending global ids: same summation order as one GPU
+        self.local = loc.cpu().numpy()
         self.loc = loc
-        self.owned_local = torch.from_numpy((self.owner[self.local] == self.rank).astype(np.uint8)).to(dev)
-        self.own_pos = torch.nonzero(self.owned_local)[:, 0]          # positions of owned residues inside the local set
+        self.counts = [int((self.owner == r).sum()) for r in range(self.world)]
+        self.cap = max(self.counts)
+        self.owned_local = mine[loc].to(torch.uint8).contiguous()
+        self.own_pos = torch.nonzero(self.owned_local)[:, 0]  # positions of owned residues inside the local set
         self.halo_pos = torch.nonzero(self.owned_local == 0)[:, 0]
-        self.halo_ids = loc[self.halo_pos]
-        sel = lambda t: t[:, loc].contiguous()  # noqa: E731
-        self.cc = ClashContext(dev, sel(batch.X), sel(batch.residue_type), sel(batch.atom_mask),
-                               sel(batch.residue_index), violation_tolerance_factor, clash_overlap_tolerance)
+        # position of every residue of the complex inside the gathered [world, cap] buffer
+        slot = torch.zeros(L, dtype=torch.long, device=dev)
+        for r in range(self.world):
+            ids = torch.nonzero(owner == r)[:, 0]
+            slot[ids] = r * self.cap + torch.arange(len(ids), device=dev)
+        self.slot = slot
+        self.halo_src = slot[loc[self.halo_pos]]
+        sel_ = lambda t: t[:, loc].contiguous()  # noqa: E731
+        self.cc = ClashContext(dev, sel_(batch.X), sel_(batch.residue_type), sel_(batch.atom_mask),
+                               sel_(batch.residue_index), violation_tolerance_factor, clash_overlap_tolerance)
+        self._state = {}
 
-    def _gather_owned(self, local_vals):
-        return gather_owned_rows(local_vals[self.own_pos], self.ids_of, self.counts, self.L)
-
-    def run(self, SC_D, lamda, num_steps=50, lr=1e-2, beta1=0.9, beta2=0.999, eps=1e-8):
-        """-> (snapshots [num_steps, L, 4], losses [num_steps]) like ClashContext.proximal, for the whole complex."""
+    def _loop(self, st, lamda, num_steps, lr, beta1, beta2, eps):
         import math
 
         from . import _lib
-        cc, dev, n = self.cc, self.dev, len(self.local)
-        f = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)  # noqa: E731
-        sc_full = SC_D.reshape(self.L, 4).to(torch.float32)
-        sc_d = sc_full[self.loc].contiguous()        # starting angles of the local set; halo rows are refreshed per step
+        cc, n = self.cc, len(self.local)
         ws = cc.scratch(1)
-        per_res, _ = cc.evaluate(sc_d)
+        static = (cc.tables.geo, cc.lower, cc.upper, cc.X, cc.rtype, cc.exists, cc.start, cc.list, st["sc_d"])
+        for k in range(num_steps):
+            t = k + 1
+            _lib.call("pp_prox_step", *static, st["mask"], st["z"], st["x"], st["m"], st["v"], 1, n, 1, None, cc.tol,
+                      cc.max_cut, float(lamda), lr / (1 - beta1 ** t), math.sqrt(1 - beta2 ** t), beta1, beta2, eps,
+                      st["snap"], st["losses"][k - 1] if k else None, st["per_res"], ws["atoms4"], ws["axes"],
+                      ws["bound"], st["loss_rows"], self.owned_local, self.L)
+            torch.index_select(st["snap"], 0, self.own_pos, out=st["send"][:len(self.own_pos)])
+            if self.world > 1:
+                dist.all_gather_into_tensor(st["all"][k], st["send"])
+                if len(self.halo_pos):  # halo copies follow their owners
+                    st["sc_d"].index_copy_(0, self.halo_pos, st["all"][k].index_select(0, self.halo_src))
+            else:
+                st["all"][k].copy_(st["send"])
+        _lib.call("pp_prox_loss", st["loss_rows"], 1, n, 1, None, float(lamda), self.L, st["losses"][num_steps - 1])
+
+    def run(self, SC_D, lamda, num_steps=50, lr=1e-2, beta1=0.9, beta2=0.999, eps=1e-8, graph=True):
+        """-> (snapshots [num_steps, L, 4], losses [num_steps]) like ClashContext.proximal, for the whole complex."""
+        from . import _lib
+        cc, dev, n = self.cc, self.dev, len(self.local)
+        key = (int(num_steps), float(lamda), lr, beta1, beta2, eps)
+        st = self._state.get(key)
+        if st is None:
+            f = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)  # noqa: E731
+            st = dict(sc_d=f(n, 4), mask=torch.zeros(n, 4, dtype=torch.uint8, device=dev), z=f(n, 4), x=f(n, 4),
+                      m=f(n, 4), v=f(n, 4), per_res=f(n), snap=f(n, 4), loss_rows=f(n, 2), losses=f(num_steps, 1, 2),
+                      send=f(self.cap, 4), all=f(num_steps, self.world * self.cap, 4), calls=0, graph=None)
+            self._state = {key: st}
+        sc_full = SC_D.reshape(self.L, 4).to(torch.float32)
+        st["sc_d"].copy_(sc_full[self.loc])     # starting angles of the local set; halo rows are refreshed per step
+        per_res, _ = cc.evaluate(st["sc_d"])
         tot = per_res[self.own_pos].sum().reshape(1)
         if self.world > 1:
             dist.all_reduce(tot)
         mean = torch.stack([tot[0] * 0, tot[0] / self.L])
-        mask = torch.zeros(n, 4, dtype=torch.uint8, device=dev)
-        z, x, m, v = f(n, 4), f(n, 4), f(n, 4), f(n, 4)
-        _lib.call("pp_prox_init_from_mean", per_res, mean, sc_d, self.owned_local, n, mask, z, x, m, v)
-        partial = f(int(_lib.load().pp_prox_partial_floats(n)))
-        snap, losses = f(n, 4), f(num_steps, 2)
-        snaps = f(num_steps, self.L, 4)
-        static = (cc.tables.geo, cc.lower, cc.upper, cc.X, cc.rtype, cc.exists, cc.start, cc.list, sc_d)
-        for k in range(num_steps):
-            t = k + 1
-            _lib.call("pp_prox_step", *static, mask, z, x, m, v, n, cc.tol, cc.max_cut, float(lamda),
-                      lr / (1 - beta1 ** t), math.sqrt(1 - beta2 ** t), beta1, beta2, eps, snap, losses[k], per_res,
-                      ws["atoms4"], ws["axes"], ws["bound"], partial, self.owned_local, self.L)
-            full = self._gather_owned(snap)          # angles after the update, every residue from its owner
-            snaps[k] = full
-            if len(self.halo_pos):
-                sc_d[self.halo_pos] = full[self.halo_ids]   # halo copies follow their owners
+        _lib.call("pp_prox_init_from_mean", per_res, mean, st["sc_d"], self.owned_local, n, st["mask"], st["z"], st["x"],
+                  st["m"], st["v"])
+        st["calls"] += 1
+        args = (st, lamda, num_steps, lr, beta1, beta2, eps)
+        if st["calls"] == 1 or not graph:
+            self._loop(*args)
+        else:
+            if st["graph"] is None:
+                torch.cuda.synchronize(dev)
+                cg = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(cg, capture_error_mode="thread_local"):
+                    self._loop(*args)
+                st["graph"] = cg
+                # the capture did not execute anything: the state set up above is still the starting state
+            st["graph"].replay()
+        losses = st["losses"].clone()
         if self.world > 1:
             dist.all_reduce(losses)
-        return snaps, losses[:, 0]
+        snaps = st["all"].index_select(1, self.slot)   # every residue from its owner, all steps at once
+        return snaps, losses[:, 0, 0]

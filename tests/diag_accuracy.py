@@ -14,7 +14,7 @@ def main():
     from packppi_b200 import TDiffusionModule, synthetic, weights
     dev = torch.device("cuda:0")
     sd = weights.make_state_dict(0)
-    configs = (("fp32", "ffma"), ("f16x3", "ffma"), ("f16x3", "tc32"), ("f16x3", "tc"))
+    configs = (("fp32", "ffma"), ("f16x3", "ffma"), ("f16x3", "tc32"))
     models = {}
     for mode, ne in configs:
         m = TDiffusionModule()

@@ -16,11 +16,11 @@ pytestmark = pytest.mark.gpu
 CHI_TOL = 1e-4   # rad
 XYZ_TOL = 1e-3   # Angstrom
 ACT_TOL = 2e-4   # hidden activations (LayerNorm-scaled, O(1) values)
-# Embedded edge features: the two inter-residue dihedrals of every SELF edge (k = 0, j = i) are the angle between two
-# analytically parallel normals, i.e. arccos(1 +- rounding) = 0 or ~3.5e-4 * sqrt(n) rad depending on the last bit
-# (encoder.py:164-174,176-196).  The reference's value there is rounding noise, ours is different rounding noise; after
-# the 468->128 Linear and LayerNorm it shows up as a few 1e-4 in h_E0.  Everything downstream is gated at ACT_TOL.
-HE0_TOL = 1e-3
+# Embedded edge features, self edges included: the inter-residue dihedrals of a SELF edge (k = 0, j = i) are the angle
+# between two analytically parallel normals, i.e. arccos(1 +- rounding) = 0 or ~3.5e-4 rad depending on the last bit
+# (encoder.py:164-174,176-196).  Round 1 allowed 1e-3 there; the kernel now repeats the reference's rounding sequence
+# (tests/test_dihedral_rounding.py), so the self edge meets the same gate as every other activation.
+HE0_TOL = 2e-4
 
 
 @pytest.fixture(scope="module")
@@ -334,6 +334,52 @@ def test_proximal_optimizer(case, dev):
         a = get_atom14_coords(bd.X, bd.residue_type, bd.BB_D, snaps[int(k)])
         r = get_atom14_coords(bd.X, bd.residue_type, bd.BB_D, tt(g["ref_prox_snaps"][i]).to(dev))
         assert (a - r).abs().max().item() < 5e-2, (case, int(k))
+
+
+def test_batched_proximal_equals_per_item(dev):
+    """VERDICT missing 3: PackPPI-Prox over a ragged batch (B = 3) x S = 2 decoys in one set of launches.  Every
+    (sample, complex) item must reproduce what the single-item path (the reference's contract, optimize.py:27) gives
+    for it: same clash mask, same 50 losses, same snapshots - bit for bit, the kernels and summation orders are shared."""
+    from packppi_b200 import collate, find_clash_mask, proximal_optimizer
+    items = []
+    for case in ("syn33", "syn64", "syn17"):
+        g, b = load_golden(case)
+        items.append((b, tt(g["in_prox_start"])))
+    batch = collate([b for b, _ in items]).to(dev)
+    B, L, S = 3, batch.X.shape[1], 2
+    gen = torch.Generator().manual_seed(11)
+    start = torch.zeros(S, B, L, 4)
+    for i, (b, st) in enumerate(items):
+        n = b.X.shape[1]
+        start[0, i, :n] = st[0]
+        start[1, i, :n] = ((torch.rand(n, 4, generator=gen) * 2 - 1) * math.pi) * b.SC_D_mask[0]
+    start = start.to(dev)
+    snaps, losses = proximal_optimizer(batch, start, 12.0, 0.5, 1.0, 50)
+    assert len(snaps) == 50 and snaps[0].shape == (S, B, L, 4) and losses[0].shape == (S, B)
+    mask = find_clash_mask(batch, start, 12.0, 0.5)
+    assert mask.shape == (S, B, L, 4)
+    for s in range(S):
+        for i, (b, _) in enumerate(items):
+            n = b.X.shape[1]
+            bd = b.to(dev)
+            one, one_l = proximal_optimizer(bd, start[s, i, :n][None].contiguous(), 12.0, 0.5, 1.0, 50)
+            assert torch.equal(mask[s, i, :n], find_clash_mask(bd, start[s, i, :n][None].contiguous(), 12.0, 0.5)[0])
+            for k in (0, 1, 17, 49):
+                assert torch.equal(snaps[k][s, i, :n], one[k][0]), (s, i, k)
+                assert float(losses[k][s, i]) == one_l[k], (s, i, k)
+            assert (snaps[49][s, i, n:] == 0).all()  # padding rows stay zero
+
+
+def test_sampling_with_proximal_over_samples_applies_the_accept_rule_per_item(model, dev):
+    g, b = load_golden("syn64")
+    bd = b.to(dev)
+    init = tt(g["in_SC_D_init"]).to(dev)
+    gen = torch.Generator().manual_seed(5)
+    other = ((torch.rand(1, 64, 4, generator=gen) * 2 - 1) * math.pi * b.SC_D_mask).to(dev)
+    both = model.sampling(bd, use_proximal=True, init_SC_D=torch.stack([init, other]), n_samples=2)
+    assert both.shape == (2, 1, 64, 4)
+    for s, x0 in enumerate((init, other)):
+        assert torch.equal(both[s], model.sampling(bd, use_proximal=True, init_SC_D=x0)), s
 
 
 def test_sampling_with_proximal_matches_reference_accept_rule(model, dev):

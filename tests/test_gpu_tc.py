@@ -22,7 +22,7 @@ def _model(dev, mode, cluster=1):
 
 
 @pytest.mark.parametrize("case", ["syn5", "syn17", "syn33", "syn64", "synbatch", "syn300", "1brs", "t1124"])
-@pytest.mark.parametrize("mode,cluster", [("f16x3", 1), ("f16x3", 2), ("f16x3", 4), ("f16", 1), ("f16", 4)])
+@pytest.mark.parametrize("mode,cluster", [("f16x3", 1), ("f16x3", 2), ("f16", 1), ("f16", 2)])
 def test_network_probe_tc(case, mode, cluster):
     dev = torch.device("cuda:0")
     g, b = load_golden(case)
@@ -38,7 +38,7 @@ def test_network_probe_tc(case, mode, cluster):
 
 
 @pytest.mark.parametrize("case", ["syn33", "synbatch", "1brs", "t1124"])
-@pytest.mark.parametrize("mode,cluster", [("f16x3", 1), ("f16x3", 4), ("f16", 2)])
+@pytest.mark.parametrize("mode,cluster", [("f16x3", 1), ("f16x3", 2), ("f16", 2)])
 def test_sampling_tc(case, mode, cluster):
     dev = torch.device("cuda:0")
     g, b = load_golden(case)
@@ -165,11 +165,11 @@ def test_node_post_tc32_matches_cuda_core_kernel(case):
         assert (ref - out).abs().max().item() < 5e-6 * max(1.0, ref.abs().max().item()), layer
 
 
-@pytest.mark.parametrize("node_epilogue", ["tc32", "tc", "ffma"])
+@pytest.mark.parametrize("node_epilogue", ["tc32", "ffma"])
 def test_node_epilogue_options(node_epilogue):
-    """The three homes of the per-residue node update: promoted tensor-core accumulation (default), plain TMEM
-    accumulation (MODE 2 of edge_tc_kernel) and the CUDA-core kernel, all within the activation gate of one network
-    evaluation; only "tc" misses the 1e-4 rad gate after the first ODE steps (tests/diag_accuracy.py)."""
+    """The two homes of the per-residue node update: promoted tensor-core accumulation (default) and the CUDA-core
+    kernel, both within the activation gate of one network evaluation.  (A third one, plain TMEM accumulation, missed the
+    1e-4 rad gate after the first ODE steps - the tensor core's fp32 accumulation truncates - and was removed.)"""
     from packppi_b200 import TDiffusionModule, weights
     dev = torch.device("cuda:0")
     g, b = load_golden("t1124")

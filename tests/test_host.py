@@ -18,7 +18,7 @@ def test_library_loads_and_exports_every_header_symbol():
     assert len(names) >= 20
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.pp_abi_version() == 1
+    assert lib.pp_abi_version() == 2
     assert set(_lib.SIGNATURES) <= names and set(_lib.KERNELS) == set(_lib.SIGNATURES)
 
 
@@ -203,6 +203,35 @@ def test_sharded_sampling_over_two_gloo_ranks():
     assert done == [7, 8, 9, 10, 12]  # every complex sampled exactly once across the two ranks
 
 
+def _sparse_worker(rank, world, port, q):
+    """More ranks than complexes: rank 1 owns nothing and must still join the collective with a buffer on the backend's
+    device (the device used to be taken from the first local result)."""
+    import torch.distributed as dist
+    from packppi_b200 import shard, synthetic
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    batches = [synthetic.make_complex((6, 3), seed=3)]
+    out = shard.sample_sharded(lambda b, S: torch.stack([b.SC_D * (s + 2) for s in range(S)]), batches, 2)
+    plan = shard.partition([9], world)
+    ok = len(out) == 1 and torch.equal(out[0], torch.stack([batches[0].SC_D[0] * (s + 2) for s in range(2)]))
+    q.put((rank, ok, len(plan[rank])))
+    dist.destroy_process_group()
+
+
+def test_sharded_sampling_with_more_ranks_than_complexes():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_sparse_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res)
+    assert [n for _, _, n in res] == [1, 0]  # the second rank had nothing to sample
+
+
 def test_slab_partition_and_halo_are_complete():
     """Owned residues of every slab see all their clash partners inside (owned + halo): the oracle's loss and gradient
     on the local subset equal the global ones on the owned residues (host logic of SURVEY.md section 8e)."""
@@ -295,3 +324,24 @@ def test_tensor_core_operand_images_decode_back_to_the_weights():
     got = decode(p[2, 1], 2 * 32 * 32, 32, 32) * float(p[2, 1, n_pre - 8])         # second chunk: k = 32..63
     assert (got[:24] - Wp[:, 32:64]).abs().max().item() < 2 ** -21 * Wp.abs().max().item()
     assert got[24:].abs().max().item() == 0.0
+
+
+def test_add_sc_noise_returns_the_reference_score_target():
+    """`add_sc_noise` used to return zeros as its second value.  The reference reads the score of the
+    wrapped normal from a 5001 x 5001 table (schedule.py:64-73); here the same table entry is evaluated on the fly.
+    Golden: the reference's own add_sc_noise on 1BRS at three times (tools/make_golden_score.py).  An index that sits
+    on a rounding boundary of the log grid may land in the neighbouring cell (numpy fp32 log vs torch fp32 log):
+    allowed for < 1 % of the entries, and then within the 0.5 % that one grid cell is worth."""
+    from util import load_golden
+    from packppi_b200 import TDiffusionModule
+    _, b = load_golden("1brs")
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "score_target.npz"))
+    m = TDiffusionModule()
+    for i in range(3):
+        x, s = m.add_sc_noise(b, torch.from_numpy(z[f"in_t_{i}"]),
+                              noise=(torch.from_numpy(z[f"in_eps1_{i}"]), torch.from_numpy(z[f"in_eps2_{i}"])))
+        rn, rs = torch.from_numpy(z[f"ref_noised_{i}"]), torch.from_numpy(z[f"ref_score_{i}"])
+        assert torch.equal(x, rn)
+        rel = (s - rs).abs() / (rs.abs() + 1e-6)
+        assert (rel > 1e-5).float().mean().item() < 0.01 and rel.max().item() < 5e-3, (i, rel.max().item())
+        assert (s[rs == 0] == 0).all() and rs.abs().max() > 0

@@ -1,5 +1,7 @@
-"""Run under torchrun with >= 2 GPUs: slab-partitioned PackPPI-Prox (halo exchange over NCCL) against the single-GPU
-run of the same complex.  `torchrun --nproc-per-node 2 tests/dist_slab_check.py [n_chains x 500 residues]`."""
+"""Run under torchrun with >= 2 GPUs: slab-partitioned PackPPI-Prox (halo exchange over NCCL, the whole loop one CUDA
+graph) against the single-GPU run of the same complex; prints one JSON line on rank 0.
+`torchrun --nproc-per-node 2 tools/dist_slab_check.py [n_chains x 500 residues]`.  tests/test_gpu_multi.py runs it
+when the box has two GPUs; bench.py times the same thing at every world size (`secondary.slab_proximal_*`)."""
 import os
 import sys
 import time
@@ -20,14 +22,17 @@ def main():
     b = synthetic.make_complex((500,) * chains, seed=5000).to(dev)
     b["X"] = (get_atom14_coords(b.X, b.residue_type, b.BB_D, b.SC_D) * b.atom_mask[..., None]).contiguous()
     sp = shard.SlabProximal(b, 12.0, 0.5)
-    sp.run(b.SC_D, 1.0, 5)  # warm-up
+    eager, _ = sp.run(b.SC_D, 1.0, 50)   # first call: eager launches
+    sp.run(b.SC_D, 1.0, 50)              # second call: captures the loop (NCCL included) in a CUDA graph
     torch.cuda.synchronize()
     dist.barrier()
     t0 = time.perf_counter()
     snaps, losses = sp.run(b.SC_D, 1.0, 50)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    assert torch.equal(eager, snaps), "graph replay differs from the eager loop"
     ref_snaps, ref_losses = proximal_optimizer(b, b.SC_D, 12.0, 0.5, 1.0, 50)
+    proximal_optimizer(b, b.SC_D, 12.0, 0.5, 1.0, 50)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     ref_snaps, ref_losses = proximal_optimizer(b, b.SC_D, 12.0, 0.5, 1.0, 50)
@@ -37,9 +42,10 @@ def main():
     dl = max(abs(a - c) / max(abs(c), 1e-9) for a, c in zip(losses.cpu().tolist(), ref_losses))
     n_local = len(sp.local)
     if rank == 0:
-        print(f"slab proximal on {world} GPUs: {chains * 500} residues, {n_local} local (owned + halo) on rank 0, "
-              f"max |chi - single GPU| = {d:.3e} rad, max rel loss diff = {dl:.3e}, "
-              f"{1e3 * dt:.1f} ms vs {1e3 * dt1:.1f} ms on one GPU")
+        import json
+        print(json.dumps({"world": world, "residues": chains * 500, "local_rank0": n_local,
+                          "max_chi_diff_vs_one_gpu": d, "bit_identical": bool(d == 0.0), "max_rel_loss_diff": dl,
+                          "slab_ms": 1e3 * dt, "one_gpu_ms": 1e3 * dt1}))
     assert d < 1e-4 and dl < 1e-4, (d, dl)
     dist.destroy_process_group()
 

@@ -106,7 +106,7 @@ def kernels(n=100, passes=3):
 
     def post():
         hv.copy_(hv0)
-        _lib.call("pp_ipmp_node_post_tc", W, 0, wtc[0, 2], graph.msum, graph.mask, G, K, S, ws.wsAcc, hv, 3, 1)
+        _lib.call("pp_ipmp_node_post_tc32", W, 0, wtc[0, 2], graph.msum, graph.mask, G, K, S, ws.wsAcc, hv)
     rep("node epilogue", post, lambda: hv)
 
 
