@@ -87,6 +87,50 @@ def read_pdb(path, mse_to_met=True):
                 residue_index=np.array(new_idx), chain_id=np.array(cids), b_factors=np.array(bfs))
 
 
+def to_pdb(prot, keep_chains=None):
+    """PDB text of a protein record, byte for byte what the reference's `to_pdb` writes (src/utils/protein.py:207-314;
+    pinned by tests/golden/pdb_text.json): `MODEL     1`, one 80-column ATOM line per atom whose mask is >= 0.5 in
+    atom14 slot order, a TER record whenever the chain id changes and after the last residue (it takes a serial
+    number), `ENDMDL`, `END`.  Serial numbers start at 1, occupancy is 1.00, the element is the first letter of the
+    atom name.  `prot`: dict (or object) with atom_positions [L,14,3], atom_mask, aaindex, residue_index, chain_id,
+    b_factors; `keep_chains` restricts the output to those chain ids."""
+    get = (lambda k: prot[k]) if isinstance(prot, dict) else (lambda k: getattr(prot, k))
+    fields = {k: np.asarray(get(k)) for k in ("atom_mask", "aaindex", "atom_positions", "residue_index", "chain_id",
+                                              "b_factors")}
+    rt = tables.restypes()
+    if np.any(fields["aaindex"] > len(rt)):
+        raise ValueError("Invalid aaindexs.")
+    if keep_chains is not None:
+        sel = np.isin(fields["chain_id"], keep_chains)
+        fields = {k: v[sel] for k, v in fields.items()}
+    if fields["atom_positions"].shape[-2] != 14:
+        raise ValueError("Invalid number of atoms per residue.")
+    one2three = tables.names()["restype_1to3"]
+    names3 = tables.names()["atom14_names"]
+    res3 = [one2three.get(rt[int(a)], "UNK") if int(a) < len(rt) else "UNK" for a in fields["aaindex"]]
+    chain, rnum = fields["chain_id"], fields["residue_index"]
+
+    def ter(serial, i):
+        return f"{'TER':<6}{serial:>5}      {res3[i]:>3} {chain[i]:>1}{rnum[i]:>4}"
+
+    lines, serial = ["MODEL     1"], 1
+    for i in range(len(res3)):
+        if i > 0 and chain[i] != chain[i - 1]:
+            lines.append(ter(serial, i - 1))
+            serial += 1
+        for name, xyz, m, b in zip(names3[res3[i]], fields["atom_positions"][i], fields["atom_mask"][i],
+                                   fields["b_factors"][i]):
+            if m < 0.5:
+                continue
+            shown = name if len(name) == 4 else f" {name}"
+            lines.append(f"{'ATOM':<6}{serial:>5} {shown:<4}{'':>1}{res3[i]:>3} {chain[i]:>1}{rnum[i]:>4}{'':>1}   "
+                         f"{xyz[0]:>8.3f}{xyz[1]:>8.3f}{xyz[2]:>8.3f}{1.0:>6.2f}{b:>6.2f}          {name[0]:>2}{'':>2}")
+            serial += 1
+    lines.append(ter(serial, len(res3) - 1))
+    lines += ["ENDMDL", "END"]
+    return "\n".join(line.ljust(80) for line in lines) + "\n"
+
+
 def write_pdb(protein, path=None):
     """ATOM/TER/END records for atom14 coordinates (same record layout as protein.py:207-314)."""
     rt = tables.restypes()

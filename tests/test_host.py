@@ -345,3 +345,60 @@ def test_add_sc_noise_returns_the_reference_score_target():
         rel = (s - rs).abs() / (rs.abs() + 1e-6)
         assert (rel > 1e-5).float().mean().item() < 0.01 and rel.max().item() < 5e-3, (i, rel.max().item())
         assert (s[rs == 0] == 0).all() and rs.abs().max() > 0
+
+
+def _ref_data_dir():
+    for d in ("/root/reference/data", os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "baseline", "_ref",
+                                                   "data")):
+        if os.path.exists(os.path.join(d, "1BRS.pdb")):
+            return d
+    return None
+
+
+@pytest.mark.skipif(_ref_data_dir() is None, reason="PDB fixtures of the reference not present")
+@pytest.mark.parametrize("name,case", [("1BRS", "1brs"), ("T1124_lig", "t1124")])
+def test_to_pdb_is_byte_identical_to_the_reference(name, case):
+    """`to_pdb` (protein.py:207-314).  Golden = sha256 of the text the reference's own to_pdb wrote for the
+    parsed file (tools/make_golden_pdb.py), plus its first / last lines and TER records for a readable failure."""
+    import hashlib
+    import json
+    from packppi_b200 import pdb
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pdb_text.json")) as f:
+        want = json.load(f)[case]
+    text = pdb.to_pdb(pdb.read_pdb(os.path.join(_ref_data_dir(), name + ".pdb")))
+    lines = text.split("\n")
+    assert lines[:4] == want["head"] and lines[-5:] == want["tail"]
+    assert [ln for ln in lines if ln.startswith("TER")] == want["ter"]
+    assert len(lines) == want["n_lines"]
+    assert hashlib.sha256(text.encode()).hexdigest() == want["sha256"]
+
+
+@pytest.mark.skipif(_ref_data_dir() is None, reason="PDB fixtures of the reference not present")
+def test_interface_mask_and_metric_block_match_the_reference(tmp_path):
+    """`get_interface_mask` (helper.py:104-129) and the arithmetic of `get_metric`
+    (protein_analysis.py:53-88), against values the reference computed (tools/make_golden_pdb.py)."""
+    from oracle import prox_oracle as po
+    from packppi_b200 import featurize, metrics, pdb
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metric_block.npz"))
+    d = _ref_data_dir()
+    for name, case in (("1BRS", "1brs"), ("T1124_lig", "t1124")):
+        path = os.path.join(d, name + ".pdb")
+        prot = pdb.read_pdb(path)
+        mask = metrics.interface_mask(prot, path)
+        b = featurize.protein_to_batch(prot)
+        assert np.array_equal((mask * b.residue_mask[0]).numpy(), z[f"{case}_interface_mask"]), case
+    # metric block: true = 1BRS, predicted = the reference-written structure with perturbed side chains
+    path = os.path.join(d, "1BRS.pdb")
+    prot = pdb.read_pdb(path)
+    true = featurize.protein_to_batch(prot)
+    true["interface_mask"] = (metrics.interface_mask(prot, path) * true.residue_mask[0])[None]
+    pred_prot = dict(prot)
+    pred_prot["atom_positions"] = z["1brs_pred_atom_positions"]
+    pred_path = tmp_path / "pred.pdb"
+    pred_path.write_text(pdb.to_pdb(pred_prot))
+    pred = featurize.protein_to_batch(pdb.read_pdb(str(pred_path)))
+    got = metrics.get_metric(true, pred, clashscore=7.25, atom14_fn=po.atom14_coords)  # host tensors: CPU rebuild
+    keys = [k[len("1brs_metric_"):] for k in z.files if k.startswith("1brs_metric_")]
+    assert set(keys) == set(got) and len(keys) == 16
+    for k in keys:
+        assert abs(float(got[k]) - float(z["1brs_metric_" + k])) <= 1e-5 * max(1.0, abs(float(z["1brs_metric_" + k]))), k
