@@ -102,12 +102,17 @@ int pp_ipmp_edge_edge(const float* weights, int64_t layer, const float* geo, con
  * msum [G] = mean of mask_attend over K (pp_knn_build): tiles whose residues all have msum == 0 (padding) are
  * skipped and their output rows left untouched (cluster == 1; zero the buffers once, the kernels of this library
  * never write anything else there).  out = accsum [S*G][128] or hE_out [S*G][K][128]; hE_in / hE_out
- * move through TMA tensor copies and must be 16-byte aligned. */
+ * move through TMA tensor copies and must be 16-byte aligned.
+ * overflow (device int32, may be NULL; the same argument of pp_ipmp_node_pre_tc / pp_ipmp_node_post_tc32): the split
+ * into fp16 halves has no per-tile scale, so an activation above 65504 becomes inf, the product NaN, and a ReLU would
+ * turn that into a plausible 0.  A kernel that splits such a value ORs 1 into *overflow (never clears it): the caller
+ * zeroes the flag, reads it after the pass and repeats the work in fp32 if it is set. */
 int64_t pp_tc_stream_floats(void);
 int pp_ipmp_edge_tc(const float* weights, int64_t layer, int64_t path, const float* wstream, const float* geo,
                     const int32_t* nbr, const float* mask_attend, const float* msum, int64_t G, int64_t K,
                     int64_t S, const float* hE_in, int64_t he_shared, const float* wsA, const float* wsN,
-                    const float* wsP, float* out, int64_t passes, int64_t cluster, pp_stream_t stream);
+                    const float* wsP, float* out, int64_t passes, int64_t cluster, int32_t* overflow,
+                    pp_stream_t stream);
 
 /* pp_ipmp_node_post on the tensor cores with fp32-grade ("promoted") accumulation: every K = 16 step of a GEMM goes
  * into a fresh TMEM accumulator and the row threads sum the steps in fp32 registers, because the tensor core's own
@@ -115,7 +120,7 @@ int pp_ipmp_edge_tc(const float* weights, int64_t layer, int64_t path, const flo
  * [S*G][128] is updated in place (reference layers.py:127-132). */
 int pp_ipmp_node_post_tc32(const float* weights, int64_t layer, const float* wstream, const float* msum,
                            const float* residue_mask, int64_t G, int64_t K, int64_t S, const float* wsAcc, float* hV,
-                           pp_stream_t stream);
+                           int32_t* overflow, pp_stream_t stream);
 
 /* Tensor-core version of pp_ipmp_node_pre (reference layers.py:72-77,91 and the h_V_i / h_V_j columns of W_in):
  * tile = 128 residue rows, the three weight matrices resident in shared memory as fp16 (hi, lo) images.
@@ -123,7 +128,7 @@ int pp_ipmp_node_post_tc32(const float* weights, int64_t layer, const float* wst
 int64_t pp_tc_pre_stream_floats(void);
 int pp_ipmp_node_pre_tc(const float* weights, int64_t layer, int64_t path, const float* wstream, const float* geo,
                         int64_t G, int64_t S, const float* hV, float* wsA, float* wsN, float* wsP,
-                        pp_stream_t stream);
+                        int32_t* overflow, pp_stream_t stream);
 
 /* Diagnostics: later pp_ipmp_edge_tc launches write clock64() stamps of the phase boundaries of their first tile
  * (CTA 0, one worker thread) into trace (device memory, >= 32 uint64); NULL switches it off. */

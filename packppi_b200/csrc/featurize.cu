@@ -13,15 +13,22 @@ namespace pp {
 struct V3 {
   float x, y, z;
 };
-__device__ __forceinline__ V3 sub(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+// Every operation below is rounded where torch-CPU rounds it (measured, see csrc/encoder.cu and
+// tests/test_dihedral_rounding.py): cross = fma(a1, b2, -rn(a2 b1)), norm = sqrt(fma(z, z, fma(y, y, rn(x x)))),
+// (a * b).sum(-1) = (rn(a0 b0) + rn(a1 b1)) + rn(a2 b2).  acos is ill-conditioned near +-1 (d acos = d c / sin), so a
+// cosine that differs in the last bit moves a near-planar dihedral by ~3e-4 rad; with the same bits it cannot.
+__device__ __forceinline__ V3 sub(V3 a, V3 b) { return {__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z)}; }
 __device__ __forceinline__ V3 cross(V3 a, V3 b) {
-  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+  return {__fmaf_rn(a.y, b.z, -__fmul_rn(a.z, b.y)), __fmaf_rn(a.z, b.x, -__fmul_rn(a.x, b.z)),
+          __fmaf_rn(a.x, b.y, -__fmul_rn(a.y, b.x))};
 }
-__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float dot(V3 a, V3 b) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
+}
 // t / |t| with nan_to_num: NaN -> 0 (helper.py:16-18); an infinite component cannot occur for finite / NaN input
 __device__ __forceinline__ V3 unit(V3 t) {
-  const float n = sqrtf(t.x * t.x + t.y * t.y + t.z * t.z);
-  V3 r = {t.x / n, t.y / n, t.z / n};
+  const float n = __fsqrt_rn(__fmaf_rn(t.z, t.z, __fmaf_rn(t.y, t.y, __fmul_rn(t.x, t.x))));
+  V3 r = {__fdiv_rn(t.x, n), __fdiv_rn(t.y, n), __fdiv_rn(t.z, n)};
   if (!(isfinite(r.x) && isfinite(r.y) && isfinite(r.z))) {
     r.x = isfinite(r.x) ? r.x : 0.f;
     r.y = isfinite(r.y) ? r.y : 0.f;

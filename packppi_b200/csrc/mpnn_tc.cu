@@ -88,6 +88,7 @@ struct Args {
   const float *A, *Nn, *pglob;
   const float* msum;                 // mean attention mask [G]: 0 marks a padding residue
   float* out;             // node path: accsum [R][128]; edge path: hE_out [R][K][128]
+  int* overflow;              // optional: set to 1 if an activation left the fp16 range (see umma.cuh)
   unsigned long long* trace;  // optional: clock64 stamps of one tile of CTA 0 (pp_set_tc_trace), else null
   int trace_it;               // which tile of the CTA (0 = first: the stamps include the prologue)
 };
@@ -140,14 +141,14 @@ __device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
 // write this thread's row of a chunk (kc columns, v[0..kc)) into an A ring slot in the UMMA core-matrix layout:
 // 8 fp16 values = one 16-byte core-matrix row; the 32 lanes of a warp write 512 contiguous bytes (conflict-free)
 template <int PASSES>
-__device__ __forceinline__ void put_chunk(uint8_t* slot, int m, const float* v, int kc) {
+__device__ __forceinline__ void put_chunk(uint8_t* slot, int m, const float* v, int kc, float& amax) {
   const int base = (m >> 3) * 128 + (m & 7) * 16;
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     if (u * 8 < kc) {
       uint4 h, l;
-      split_f16x2(v[u * 8 + 0], v[u * 8 + 1], h.x, l.x); split_f16x2(v[u * 8 + 2], v[u * 8 + 3], h.y, l.y);
-      split_f16x2(v[u * 8 + 4], v[u * 8 + 5], h.z, l.z); split_f16x2(v[u * 8 + 6], v[u * 8 + 7], h.w, l.w);
+      split_f16x2(v[u * 8 + 0], v[u * 8 + 1], h.x, l.x, amax); split_f16x2(v[u * 8 + 2], v[u * 8 + 3], h.y, l.y, amax);
+      split_f16x2(v[u * 8 + 4], v[u * 8 + 5], h.z, l.z, amax); split_f16x2(v[u * 8 + 6], v[u * 8 + 7], h.w, l.w, amax);
       *reinterpret_cast<uint4*>(slot + u * kLbo + base) = h;
       if (PASSES == 3) *reinterpret_cast<uint4*>(slot + kImgBytes + u * kLbo + base) = l;
     }
@@ -457,6 +458,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
       return tot;
     };
     uint32_t sf_phase = 0;
+    float amax = 0.f;  // largest magnitude this thread split into fp16 halves (overflow report)
     // this thread's row in the staging buffer; 16-byte unit u of chunk c sits at (c << 14) + ((u ^ (k & 7)) << 4)
     uint8_t* const srow = stage + (rl << 12) + (k << 7);
     const int swz = k & 7;
@@ -464,7 +466,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
     auto publish = [&](int q, const float* vals, int kc) {
       const int slot = q % kSA;
       mbar_wait(&a_empty[slot], ((q / kSA) & 1) ^ 1);
-      put_chunk<PASSES>(Aring + slot * kSlotBytes, m, vals, kc);
+      put_chunk<PASSES>(Aring + slot * kSlotBytes, m, vals, kc, amax);
       fence_async_smem();
       mbar_arrive(&a_full[slot]);
     };
@@ -693,7 +695,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = (x[t][i] - mean) * rstd * gm[i] + bt[i];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) split_f16x2(v[2 * i], v[2 * i + 1], eh[i], el[i]);
+            for (int i = 0; i < 16; ++i) split_f16x2(v[2 * i], v[2 * i + 1], eh[i], el[i], amax);
             store_tmem(RE + c * 32, v);
             tmem_st16(PK + lane_base + c * 16, eh);
             if (PASSES == 3) tmem_st16(PK + 64 + lane_base + c * 16, el);
@@ -782,6 +784,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
       cx = nx;
       tile = nxt_tile;
     }  // tile loop
+    report_overflow(a.overflow, amax);
   }
 
   // ---- teardown: all tensor-core work of this CTA has been consumed by its workers; in a cluster nobody may exit
@@ -894,7 +897,8 @@ extern "C" int pp_set_tc_trace(uint64_t* trace) {
 extern "C" int pp_ipmp_edge_tc(const float* weights, int64_t layer, int64_t path, const float* wstream,
                                const float* geo, const int32_t* nbr, const float* mask_attend, const float* msum,
                                int64_t G, int64_t K, int64_t S, const float* hE_in, int64_t he_shared, const float* wsA, const float* wsN,
-                               const float* wsP, float* out, int64_t passes, int64_t cluster, cudaStream_t stream) {
+                               const float* wsP, float* out, int64_t passes, int64_t cluster, int32_t* overflow,
+                               cudaStream_t stream) {
   PP_REQUIRE(weights && wstream && geo && nbr && mask_attend && msum && hE_in && wsA && wsN && wsP && out,
              "null pointer");
   PP_REQUIRE(layer >= 0 && layer < 3 && (path == 0 || path == 1), "layer / path out of range");
@@ -914,6 +918,7 @@ extern "C" int pp_ipmp_edge_tc(const float* weights, int64_t layer, int64_t path
   a.hE_in = hE_in; a.he_shared = (int)he_shared;
   a.A = wsA; a.Nn = wsN; a.pglob = wsP;
   a.out = out;
+  a.overflow = overflow;
   a.trace = path == g_tc_trace_path ? g_tc_trace : nullptr;  // the trace follows one of the two kernels
   a.trace_it = g_tc_trace_it;
   int rc;

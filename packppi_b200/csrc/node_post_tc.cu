@@ -57,15 +57,16 @@ struct Args {
   const float* accsum;        // [R][128] summed messages
   float in_scale;             // 1 / K
   float* hV;                  // [R][128], updated in place
+  int* overflow;              // optional overflow flag (umma.cuh: report_overflow)
 };
 
-__device__ __forceinline__ void put_chunk(uint8_t* slot, int m, const float* v) {
+__device__ __forceinline__ void put_chunk(uint8_t* slot, int m, const float* v, float& amax) {
   const int base = (m >> 3) * 128 + (m & 7) * 16;
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     uint4 h, l;
-    split_f16x2(v[u * 8 + 0], v[u * 8 + 1], h.x, l.x); split_f16x2(v[u * 8 + 2], v[u * 8 + 3], h.y, l.y);
-    split_f16x2(v[u * 8 + 4], v[u * 8 + 5], h.z, l.z); split_f16x2(v[u * 8 + 6], v[u * 8 + 7], h.w, l.w);
+    split_f16x2(v[u * 8 + 0], v[u * 8 + 1], h.x, l.x, amax); split_f16x2(v[u * 8 + 2], v[u * 8 + 3], h.y, l.y, amax);
+    split_f16x2(v[u * 8 + 4], v[u * 8 + 5], h.z, l.z, amax); split_f16x2(v[u * 8 + 6], v[u * 8 + 7], h.w, l.w, amax);
     *reinterpret_cast<uint4*>(slot + u * kLbo + base) = h;
     *reinterpret_cast<uint4*>(slot + kImgBytes + u * kLbo + base) = l;
   }
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(kThreads, 1) node_post_tc_kernel(const Args a)
     const float* wsc = a.wstream + kImageFloats;  // 1 / scale of G1, G2, G3 (= W3), FFN-in, FFN-out
     const float s3 = wsc[2], sFI = wsc[3], sFO = wsc[4];
     uint32_t t = 0;
+    float amax = 0.f;  // overflow report, see umma.cuh
     int q = 0;  // A chunks published so far by this thread's group schedule (kernel-wide chunk counter)
     // this thread's 16-byte units of the parked row: unit u of chunk c at row m, swizzled against bank conflicts
     uint8_t* const prow = park + m * 512;
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) node_post_tc_kernel(const Args a)
     auto publish = [&](int qq, const float* vals) {
       const int slot = qq % kSA;
       mbar_wait(&a_empty[slot], ((qq / kSA) & 1) ^ 1);
-      put_chunk(Aring + slot * kSlotBytes, m, vals);
+      put_chunk(Aring + slot * kSlotBytes, m, vals, amax);
       fence_async_smem();
       mbar_arrive(&a_full[slot]);
     };
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(kThreads, 1) node_post_tc_kernel(const Args a)
 #pragma unroll
           for (int i = 0; i < 32; ++i) ef[i] = __float_as_uint(acc[tt][i]);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) split_f16x2(acc[tt][2 * i], acc[tt][2 * i + 1], eh[i], el[i]);
+          for (int i = 0; i < 16; ++i) split_f16x2(acc[tt][2 * i], acc[tt][2 * i + 1], eh[i], el[i], amax);
           tmem_st32(RE + lane_base + c * 32, ef);
           tmem_st16(PK + lane_base + c * 16, eh);
           tmem_st16(PK + 64 + lane_base + c * 16, el);
@@ -371,6 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) node_post_tc_kernel(const Args a)
         }
       }
     }
+    report_overflow(a.overflow, amax);
   }
   fence_before_sync();
   __syncthreads();
@@ -384,10 +387,10 @@ using namespace pp;
 
 // Tensor-core node update with promoted (fp32-grade) accumulation: h_V <- mask * LN1(e + FFN(e)),
 // e = LN0(h_V + W3 mean_k(msg) + b3 mean_k(mask))  (reference layers.py:127-132).  Same arguments as
-// pp_ipmp_node_post_tc; wstream = operand images of path 2 of this layer (weights.py: pack_tc_stream).
+// pp_ipmp_node_post; wstream = operand images of path 2 of this layer (weights.py: pack_tc_stream).
 extern "C" int pp_ipmp_node_post_tc32(const float* weights, int64_t layer, const float* wstream, const float* msum,
                                       const float* residue_mask, int64_t G, int64_t K, int64_t S, const float* wsAcc,
-                                      float* hV, cudaStream_t stream) {
+                                      float* hV, int32_t* overflow, cudaStream_t stream) {
   PP_REQUIRE(weights && wstream && msum && residue_mask && wsAcc && hV, "null pointer");
   PP_REQUIRE(layer >= 0 && layer < 3, "layer out of range");
   PP_REQUIRE(G > 0 && S > 0 && K > 0 && K <= PP_KMAX, "bad sizes");
@@ -402,6 +405,7 @@ extern "C" int pp_ipmp_node_post_tc32(const float* weights, int64_t layer, const
   a.rmask = residue_mask; a.msum = msum;
   a.accsum = wsAcc; a.in_scale = 1.f / (float)K;
   a.hV = hV;
+  a.overflow = overflow;
   cudaError_t e = cudaFuncSetAttribute(post::node_post_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post::kSmem);
   if (e != cudaSuccess) {
     snprintf(g_last_error, sizeof(g_last_error), "node_post_tc_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));

@@ -43,15 +43,16 @@ struct Args {
   const float *BP, *B1;
   const float* hV;       // [R][128]
   float *A, *Nn, *P;     // wsA, wsN [R][128], wsP [R][24]
+  int* overflow;         // optional overflow flag (umma.cuh: report_overflow)
 };
 
-__device__ __forceinline__ void put_chunk(uint8_t* slot, int m, const float* v) {
+__device__ __forceinline__ void put_chunk(uint8_t* slot, int m, const float* v, float& amax) {
   const int base = (m >> 3) * 128 + (m & 7) * 16;
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     uint4 h, l;
-    split_f16x2(v[u * 8 + 0], v[u * 8 + 1], h.x, l.x); split_f16x2(v[u * 8 + 2], v[u * 8 + 3], h.y, l.y);
-    split_f16x2(v[u * 8 + 4], v[u * 8 + 5], h.z, l.z); split_f16x2(v[u * 8 + 6], v[u * 8 + 7], h.w, l.w);
+    split_f16x2(v[u * 8 + 0], v[u * 8 + 1], h.x, l.x, amax); split_f16x2(v[u * 8 + 2], v[u * 8 + 3], h.y, l.y, amax);
+    split_f16x2(v[u * 8 + 4], v[u * 8 + 5], h.z, l.z, amax); split_f16x2(v[u * 8 + 6], v[u * 8 + 7], h.w, l.w, amax);
     *reinterpret_cast<uint4*>(slot + u * kLbo + base) = h;
     *reinterpret_cast<uint4*>(slot + kImgBytes + u * kLbo + base) = l;
   }
@@ -150,10 +151,11 @@ __global__ void __launch_bounds__(kThreads, 1) node_pre_tc_kernel(const Args a) 
     const float sP = wsc[0], sA = wsc[1], sN = wsc[2];
     uint32_t ph = 0;
     int qbase = 0;
+    float amax = 0.f;  // overflow report, see umma.cuh
     auto publish = [&](int q, const float* vals) {
       const int slot = q % kSA;
       mbar_wait(&a_empty[slot], ((q / kSA) & 1) ^ 1);
-      put_chunk(Aring + slot * kSlotBytes, m, vals);
+      put_chunk(Aring + slot * kSlotBytes, m, vals, amax);
       fence_async_smem();
       mbar_arrive(&a_full[slot]);
     };
@@ -235,6 +237,7 @@ __global__ void __launch_bounds__(kThreads, 1) node_pre_tc_kernel(const Args a) 
       mbar_arrive(tile_done);
       qbase += 5;
     }
+    report_overflow(a.overflow, amax);
   }
   fence_before_sync();
   __syncthreads();
@@ -252,7 +255,7 @@ extern "C" int64_t pp_tc_pre_stream_floats() { return pre::kStreamFloats; }
 //   wstream: operand images of this layer and path, pp_tc_pre_stream_floats() floats (weights.py: pack_pre_stream)
 extern "C" int pp_ipmp_node_pre_tc(const float* weights, int64_t layer, int64_t path, const float* wstream,
                                    const float* geo, int64_t G, int64_t S, const float* hV, float* wsA, float* wsN,
-                                   float* wsP, cudaStream_t stream) {
+                                   float* wsP, int32_t* overflow, cudaStream_t stream) {
   PP_REQUIRE(weights && wstream && geo && hV && wsA && wsN && wsP, "null pointer");
   PP_REQUIRE(layer >= 0 && layer < 3 && (path == 0 || path == 1), "layer / path out of range");
   PP_REQUIRE(G > 0 && S > 0, "bad sizes");
@@ -263,6 +266,7 @@ extern "C" int pp_ipmp_node_pre_tc(const float* weights, int64_t layer, int64_t 
   a.BP = Lb + (path ? PP_OFF(L0_E_BP) : PP_OFF(L0_N_BP));
   a.B1 = Lb + (path ? PP_OFF(L0_E_B1) : PP_OFF(L0_N_B1));
   a.hV = hV; a.A = wsA; a.Nn = wsN; a.P = wsP;
+  a.overflow = overflow;
   cudaError_t e = cudaFuncSetAttribute(pre::node_pre_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre::kSmem);
   if (e != cudaSuccess) {
     snprintf(g_last_error, sizeof(g_last_error), "node_pre_tc_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));

@@ -197,6 +197,17 @@ __device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+// The same, tracking the largest magnitude that was split: an operand above kF16Max becomes inf in the hi half, the
+// product NaN, and a ReLU epilogue (fmaxf ignores NaN) would turn that into a plausible 0.  The kernels therefore
+// report it: a thread that saw amax > kF16Max sets the caller's overflow flag before it exits (report_overflow).
+constexpr float kF16Max = 65504.f;
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo, float& amax) {
+  amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(b)));
+  split_f16x2(a, b, hi, lo);
+}
+__device__ __forceinline__ void report_overflow(int* flag, float amax) {
+  if (flag != nullptr && !(amax <= kF16Max)) atomicOr(flag, 1);
+}
 
 }  // namespace umma
 }  // namespace pp

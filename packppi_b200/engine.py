@@ -194,6 +194,8 @@ class Engine:
         self.tables = DeviceTables.get(self.dev)
         self._ws = {}
         self._pool = WorkspacePool(self.dev)
+        # sticky flag the tensor-core kernels set when an activation leaves the fp16 range (include/packppi_b200.h)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self._sched = {}
 
     # ------------------------------------------------------------------ graph
@@ -257,7 +259,7 @@ class Engine:
             node_tc = self.mode != "fp32"  # residue prologue on the tensor cores
             pre = lambda path: (  # noqa: E731
                 _lib.call("pp_ipmp_node_pre_tc", W, layer, path, self.wpre[layer, path], graph.geo, G, S, ws.hV, ws.wsA,
-                          ws.wsN, ws.wsP, rows=S * G) if node_tc else
+                          ws.wsN, ws.wsP, self.overflow, rows=S * G) if node_tc else
                 _lib.call("pp_ipmp_node_pre", W, layer, path, *common, *size, ws.hV, ws.wsA, ws.wsN, ws.wsP, rows=S * G))
             pre(0)
             if self.mode == "fp32":
@@ -265,12 +267,12 @@ class Engine:
                           ws.wsAcc, rows=S * G)
             else:
                 _lib.call("pp_ipmp_edge_tc", W, layer, 0, self.wtc[layer, 0], *common, graph.msum, G, K, S, hE_in, shared, ws.wsA,
-                          ws.wsN, ws.wsP, ws.wsAcc, *tcp, rows=S * G, tag="node")
+                          ws.wsN, ws.wsP, ws.wsAcc, *tcp, self.overflow, rows=S * G, tag="node")
             if self.mode == "fp32" or self.node_epilogue == "ffma":
                 _lib.call("pp_ipmp_node_post", W, layer, *common, graph.msum, *size, ws.wsAcc, ws.hV, rows=S * G)
             else:
                 _lib.call("pp_ipmp_node_post_tc32", W, layer, self.wtc[layer, 2], graph.msum, graph.mask, G, K, S,
-                          ws.wsAcc, ws.hV, rows=S * G)
+                          ws.wsAcc, ws.hV, self.overflow, rows=S * G)
             if edge:
                 pre(1)
                 if self.mode == "fp32":
@@ -278,7 +280,7 @@ class Engine:
                               ws.hE, rows=S * G)
                 else:
                     _lib.call("pp_ipmp_edge_tc", W, layer, 1, self.wtc[layer, 1], *common, graph.msum, G, K, S, hE_in, shared,
-                              ws.wsA, ws.wsN, ws.wsP, ws.hE, *tcp, rows=S * G, tag="edge")
+                              ws.wsA, ws.wsN, ws.wsP, ws.hE, *tcp, self.overflow, rows=S * G, tag="edge")
         return ws.hV
 
     def network(self, graph, batch, chi, t):

@@ -91,6 +91,7 @@ class _PackedModule(nn.Module):
     kernel_mode = os.environ.get("PACKPPI_B200_MODE", "f16x3")
     kernel_cluster = int(os.environ.get("PACKPPI_B200_CLUSTER", "1"))
     kernel_node_epilogue = os.environ.get("PACKPPI_B200_NODE_EPILOGUE") or None
+    check_finite = os.environ.get("PACKPPI_B200_CHECK_FINITE", "1") != "0"  # overflow guard of the split-fp16 modes
 
     def _full_state_dict(self):
         raise NotImplementedError
@@ -222,6 +223,14 @@ class TDiffusionModule(_PackedModule):
 
     def _full_state_dict(self):
         return self.state_dict()
+
+    def _fp32_engine(self, device):
+        """Exact-fp32 engine with the same weights (the overflow fallback of the tensor-core modes)."""
+        sig = getattr(self, "_engine_sig", None)
+        if getattr(self, "_fp32_sig", None) != sig:
+            object.__setattr__(self, "_fp32_obj", Engine(self._full_state_dict(), device, "fp32"))
+            object.__setattr__(self, "_fp32_sig", sig)
+        return self._fp32_obj
 
     @classmethod
     def load_from_checkpoint(cls, checkpoint_path, map_location=None, strict=False, **kwargs):
@@ -361,8 +370,21 @@ class TDiffusionModule(_PackedModule):
         smp = self.hparams.sample_cfg
         if smp.mode not in ("ode", "sde"):
             raise NotImplementedError(f"sample_cfg.mode = {smp.mode!r}: the reference knows 'ode' and 'sde'")
-        chi = eng.sample(g, batch, chi0, n_steps=len(self.schedule) - 1, annealed_temp=smp.annealed_temp,
-                         mode=smp.mode, sde_noise=sde_noise, generator=generator)
+        run = lambda e: e.sample(g, batch, chi0, n_steps=len(self.schedule) - 1, annealed_temp=smp.annealed_temp,  # noqa: E731
+                                 mode=smp.mode, sde_noise=sde_noise, generator=generator)
+        check = eng.mode != "fp32" and self.check_finite
+        if check:
+            eng.overflow.zero_()
+        chi = run(eng)
+        if check and bool(eng.overflow.item()):
+            # The tensor-core modes split fp32 activations into fp16 (hi, lo) pairs without a per-tile scale: a hidden
+            # activation above 65504 (possible with an unusually scaled checkpoint; never seen with xavier-initialised or
+            # LayerNorm-bounded values) becomes inf, the product NaN, and the next ReLU would turn that into a plausible
+            # zero.  The kernels raise a flag when they split such a value; redo the call in exact fp32.
+            import warnings
+            warnings.warn("packppi_b200: an activation left the fp16 range in the split-fp16 tensor-core mode; repeating "
+                          "this call with the fp32 CUDA-core kernels")
+            chi = run(self._fp32_engine(dev))
         SC_D_sample = chi.reshape(S, B, L, 4) if n_samples is not None else chi.reshape(B, L, 4)
         if not use_proximal:
             return SC_D_sample

@@ -517,10 +517,10 @@ def test_device_featurisation_matches_host(dev):
         assert h.shape == d.shape and h.dtype == d.dtype, k
         if k in exact:
             assert torch.equal(h, d), k
-        elif k in ("BB_D", "SC_D"):
-            assert wrapped_diff(d, h).max().item() < 2e-4, (k, wrapped_diff(d, h).max().item())
+        elif k in ("BB_D", "SC_D"):  # same rounding sequence as torch-CPU up to acos itself (a few ulp of pi)
+            assert wrapped_diff(d, h).max().item() < 1e-5, (k, wrapped_diff(d, h).max().item())
         else:
-            assert (h - d).abs().max().item() < 2e-4, (k, (h - d).abs().max().item())
+            assert (h - d).abs().max().item() < 1e-5, (k, (h - d).abs().max().item())
     # the sampled angles from either batch agree to the usual gate once the inputs agree
     assert wrapped_diff(devb.SC_D.cpu(), host.SC_D).mean().item() < 2e-6
 

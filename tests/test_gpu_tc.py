@@ -134,7 +134,7 @@ def test_node_pre_tc_matches_cuda_core_kernel(case):
             out = [torch.full((S * G, n), float("nan"), device=dev) for n in (128, 128, 24)]
             _lib.call("pp_ipmp_node_pre", W, layer, path, graph.geo, graph.nbr, graph.mask_attend, graph.mask, G, K, S,
                       hV, *ref)
-            _lib.call("pp_ipmp_node_pre_tc", W, layer, path, eng.wpre[layer, path], graph.geo, G, S, hV, *out)
+            _lib.call("pp_ipmp_node_pre_tc", W, layer, path, eng.wpre[layer, path], graph.geo, G, S, hV, *out, None)
             torch.cuda.synchronize()
             for name, r, o in zip(("A", "N", "P"), ref, out):
                 scale = max(1.0, r.abs().max().item())
@@ -159,7 +159,7 @@ def test_node_post_tc32_matches_cuda_core_kernel(case):
         ref, out = hV0.clone(), hV0.clone()
         _lib.call("pp_ipmp_node_post", W, layer, graph.geo, graph.nbr, graph.mask_attend, graph.msum, graph.mask, G, K,
                   S, acc, ref)
-        _lib.call("pp_ipmp_node_post_tc32", W, layer, eng.wtc[layer, 2], graph.msum, graph.mask, G, K, S, acc, out)
+        _lib.call("pp_ipmp_node_post_tc32", W, layer, eng.wtc[layer, 2], graph.msum, graph.mask, G, K, S, acc, out, None)
         torch.cuda.synchronize()
         assert torch.isfinite(out).all()
         assert (ref - out).abs().max().item() < 5e-6 * max(1.0, ref.abs().max().item()), layer
@@ -218,3 +218,30 @@ def test_random_shapes_tensor_cores_match_cuda_cores(seed):
     assert torch.isfinite(res["f16x3"][1]).all()
     assert (res["fp32"][1] - res["f16x3"][1]).abs().max().item() < TOL["f16x3"]["act"], (B, L, S)
     assert (res["fp32"][0] - res["f16x3"][0]).abs().max().item() < TOL["f16x3"]["act"], (B, L, S)
+
+
+def test_fp16_overflow_is_detected_and_redone_in_fp32():
+    """the split-fp16 operands carry no per-tile scale, so a checkpoint whose hidden activations exceed
+    65504 overflows.  Contract: never a silently wrong angle - the result is NaN inside the kernels, `sampling` notices
+    and repeats the call with the fp32 kernels."""
+    import warnings
+    from packppi_b200 import TDiffusionModule, weights
+    dev = torch.device("cuda:0")
+    g, b = load_golden("syn33")
+    sd = weights.make_state_dict(0)
+    sd = {k: v.clone() for k, v in sd.items()}
+    sd["mpnn.mpnn_layers.0.edge_dense.W_in.weight"] *= 1e6   # FFN hidden of the first edge update ~ 1e6 > 65504
+    sd["mpnn.mpnn_layers.0.edge_dense.W_out.weight"] /= 1e6
+    init = tt(g["in_SC_D_init"]).to(dev)
+    outs = {}
+    for mode in ("f16x3", "fp32"):
+        m = TDiffusionModule()
+        m.load_state_dict(sd)
+        m.kernel_mode = mode
+        m = m.to(dev).eval()
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            outs[mode] = m.sampling(b.to(dev), init_SC_D=init)
+        assert (len([x for x in w if "fp16 range" in str(x.message)]) == 1) == (mode == "f16x3"), mode
+    assert torch.isfinite(outs["f16x3"]).all()
+    assert torch.equal(outs["f16x3"], outs["fp32"])
