@@ -142,11 +142,13 @@ int pp_set_tc_trace_tile(int64_t path, int64_t it);
  *   chi <- wrap(chi + [step_mask] c_ode (score * w_anneal)) * chi_mask.
  * score_out [S*G][4] or NULL; step_mask uint8 [G][4]; chi_mask [G][4]; chi [S*G][4] in/out.
  * SDE branch (schedule.py:224-228) when noise_1pi / noise_2pi [S*G][4] (the two torch.normal draws of a step) and
- * mask_1pi uint8 [G][4] are given: chi += c_ode (score * w) + d_sde * noise with c_ode = g^2 dt, d_sde = g sqrt(dt). */
+ * mask_1pi uint8 [G][4] are given: chi += c_ode (score * w) + d_sde * noise with c_ode = g^2 dt, d_sde = g sqrt(dt).
+ * With d_sde != 0 and the noise pointers NULL the normals are generated in the kernel: Philox4x32-10 keyed by `seed`,
+ * counter (row, step_index) - one independent stream per (item, step), nothing stored. */
 int pp_decode_step(const float* weights, const float* hV, int64_t G, int64_t S, float* score_out, int64_t do_step,
                    float c_ode, float w_anneal, const uint8_t* step_mask, const float* chi_mask, float* chi,
-                   const float* noise_1pi, const float* noise_2pi, const uint8_t* mask_1pi, float d_sde,
-                   pp_stream_t stream);
+                   const float* noise_1pi, const float* noise_2pi, const uint8_t* mask_1pi, float d_sde, int64_t seed,
+                   int64_t step_index, pp_stream_t stream);
 
 /* get_atom14_coords (models/components/__init__.py:76-120).  tables [21][pp_table_stride()] from
  * packppi_b200.tables.packed_geometry(); chi [S*G][4] -> xyz_out [S*G][14][3]. */

@@ -290,7 +290,7 @@ class Engine:
         ni = graph.ni if getattr(graph, "ni", None) is not None else self.node_inputs(batch)
         self.forward_layers(graph, ws, ni, chi, t, 1)
         _lib.call("pp_decode_step", self.wblob, ws.hV, graph.G, S, ws.score, 0, 0.0, 0.0, None, None, None, None, None,
-                  None, 0.0)
+                  None, 0.0, 0, 0)
         return ws.score, ws.hV
 
     # ------------------------------------------------------------------ sampling
@@ -326,14 +326,15 @@ class Engine:
             self._sched[key] = (coefs, torch.tensor([c[0] for c in coefs], dtype=torch.float32, device=self.dev))
         return self._sched[key]
 
-    def _run_steps(self, graph, ws, ni, step_mask, chi, tvals, coefs, trajectory=None, sde=None):
-        """sde = (mask_1pi uint8 [G,4], noise [steps, 2, S*G, 4]) switches the update to the SDE branch."""
+    def _run_steps(self, graph, ws, ni, step_mask, chi, tvals, coefs, trajectory=None, sde=None, seed=0):
+        """sde = (mask_1pi uint8 [G,4], noise [steps, 2, S*G, 4]) switches the update to the SDE branch with injected
+        draws; sde = None with non-zero diffusion coefficients uses the in-kernel Philox stream of `seed`."""
         G, S = graph.G, ws.S
         for j, (_, c, w, d) in enumerate(coefs):
             self.forward_layers(graph, ws, ni, chi, tvals[j:j + 1], 0)
             n1, n2, m1 = (sde[1][j, 0], sde[1][j, 1], sde[0]) if sde is not None else (None, None, None)
             _lib.call("pp_decode_step", self.wblob, ws.hV, G, S, None, 1, c, w, step_mask, ni["chi_mask"], chi, n1, n2,
-                      m1, d)
+                      m1, d, int(seed), j)
             if trajectory is not None:
                 trajectory.append(chi.clone())
 
@@ -353,11 +354,17 @@ class Engine:
             step_mask = (batch.chi_1pi_periodic_mask.to(self.dev).reshape(-1, 4).bool() |
                          batch.chi_2pi_periodic_mask.to(self.dev).reshape(-1, 4).bool()).to(torch.uint8).contiguous()
         coefs, tvals = self._schedule(n_steps, annealed_temp, mode)
-        if mode == "sde":  # fresh noise every step: no graph replay; `sde_noise` [steps, 2, S*G, 4] injects the draws
-            if sde_noise is None:
-                sde_noise = torch.randn(n_steps, 2, S * G, 4, device=self.dev, generator=generator)
-            m1 = batch.chi_1pi_periodic_mask.to(self.dev).reshape(-1, 4).to(torch.uint8).contiguous()
+        if mode == "sde":  # fresh noise every step: no graph replay
             chi = chi_init.clone().contiguous()
+            if sde_noise is None:
+                # one Philox stream per (row, step) inside the decode kernel, keyed by a seed drawn from `generator`
+                # (or torch's default CPU generator): nothing of size [steps, 2, rows, 4] is materialised
+                gdev = generator.device if generator is not None else torch.device("cpu")
+                seed = int(torch.randint(0, 2 ** 62, (1,), device=gdev, generator=generator).item())
+                self._run_steps(graph, self.workspace(G, K, S), ni, step_mask, chi, tvals, coefs, trajectory, seed=seed)
+                return chi
+            m1 = graph.mask_1pi if getattr(graph, "mask_1pi", None) is not None else \
+                batch.chi_1pi_periodic_mask.to(self.dev).reshape(-1, 4).to(torch.uint8).contiguous()
             self._run_steps(graph, self.workspace(G, K, S), ni, step_mask, chi, tvals, coefs, trajectory,
                             sde=(m1, sde_noise.to(self.dev, torch.float32).contiguous()))
             return chi
