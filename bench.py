@@ -173,6 +173,7 @@ class ReferenceCPU:
 
     def __init__(self, threads):
         sys.path.insert(0, os.path.join(ROOT, "tools"))
+        os.environ.setdefault("TQDM_DISABLE", "1")  # the reference builds its score tables under tqdm progress bars
         import ref_shims
         from packppi_b200 import weights
         if not ref_shims.available():
@@ -235,6 +236,21 @@ def run_reference(args):
     so the rate is that of a length-stratified sample of the workload.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if "WORLD_SIZE" in os.environ and os.environ.get("PP_BENCH_REFERENCE_CHILD") != "1":
+        # Under torchrun every rank inherits OMP_NUM_THREADS=1 (read when the OpenMP runtime starts, i.e. at `import
+        # torch`), which would pin the reference to one core.  Rank 0 re-runs this arm in a fresh interpreter without the
+        # launcher's environment and relays its line; the other ranks have already left.
+        env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "RANK", "WORLD_SIZE",
+                                                                "LOCAL_RANK", "LOCAL_WORLD_SIZE", "GROUP_RANK",
+                                                                "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID")}
+        env["PP_BENCH_REFERENCE_CHILD"] = "1"
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--gpus", str(args.gpus),
+                              "--steps", str(args.steps), "--warmup", str(args.warmup), "--complexes",
+                              str(args.complexes)], env=env, capture_output=True, text=True)
+        sys.stderr.write(out.stderr[-2000:])
+        lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+        print(lines[-1] if lines else json.dumps({"impl": "reference", "unavailable": "child run failed"}))
         return
     threads = os.cpu_count() or 1
     items = sweep_items(args.complexes)
@@ -651,7 +667,7 @@ def main():
         secondary.update(slab)
 
     cpu = parity = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:  # the CPU arm is a single-process measurement (N = 1)
         arm = cpu_arm(os.cpu_count() or 1)
         picks = stratified(items, 4)
         res, secs, check = 0, 0.0, None
