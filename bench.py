@@ -280,9 +280,8 @@ def run_reference(args):
               f"complex of the sweep per bench step, {min(b.max_size for b in timed)}-{max(b.max_size for b in timed)} "
               f"residues spread evenly over the length-sorted sweep{bounded}; {res} residues, {secs:.1f} s; "
               f"CPU: {cpu_model_name()}")
-    cfg = workload_config(args)
-    cfg["reference_sample"] = sample
-    line = {"impl": "reference", "metric": "residue.denoise-steps/s", "value": value, "unit": "residue.steps/s",
+    cfg = workload_config(args)  # the same workload description as our arm; what was actually timed: `sample`
+    line = {"impl": "reference", "sample": sample, "metric": "residue.denoise-steps/s", "value": value, "unit": "residue.steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg,
@@ -307,7 +306,9 @@ def workload_config(args):
                            "fp32": "fp32 FFMA on CUDA cores",
                            "f16": "fast mode: plain fp16 tensor-core inputs, fp32 accumulation (own tolerance 2e-2 rad)"
                            }.get(os.environ.get("PACKPPI_B200_MODE", "f16x3"), "see kernel_mode"),
-            "parallelism": "one sweep per GPU, no data-path collective"}
+            "parallelism": (f"the fixed sweep partitioned over {args.gpus} rank(s) by residue count "
+                            "(packppi_b200.shard.partition), no data-path collective, one all_gather_into_tensor of "
+                            "the sampled angles per step")}
 
 
 def _events_ms(fn, reps):
@@ -691,9 +692,6 @@ def main():
 
     if rank == 0:
         cfg = workload_config(args)
-        cfg["parallelism"] = (f"the fixed sweep partitioned over {world} rank(s) by residue count "
-                              "(packppi_b200.shard.partition), no data-path collective, one all_gather_into_tensor of "
-                              "the sampled angles per step")
         line = {"metric": "residue.denoise-steps/s", "value": value, "unit": "residue.steps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": DTYPE.get(mode, mode), "data": "synthetic",
