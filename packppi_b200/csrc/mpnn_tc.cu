@@ -196,20 +196,25 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
   // iterations past the last tile work on fully masked rows
   const int niter = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
   constexpr uint16_t kMask = (uint16_t)((1u << CLUSTER) - 1);
-  // A CTA that owns its weight stream skips tiles whose four residues are all padding (mean attention mask 0): every
-  // role walks the same sequence of live tiles.  The output rows of skipped tiles are not written: the caller keeps
-  // them zero (nothing but the skipped tiles themselves ever reads or writes them).
+  // Tiles whose residues are all padding (mean attention mask 0) are skipped: every role walks the same sequence of
+  // live tiles.  In a cluster of 2 the CTAs share one weight stream in lockstep, so the unit of skipping is the PAIR of
+  // tiles (2t, 2t + 1) the cluster works on - both CTAs take the same decision (padding is contiguous, so pairs are
+  // almost always uniformly live or dead).  The output rows of skipped tiles are not written: the caller keeps them
+  // zero (nothing but the skipped tiles themselves ever reads or writes them).
 #ifndef PP_TC_SKIP
 #define PP_TC_SKIP 1
 #endif
-  constexpr bool SKIP = PP_TC_SKIP && CLUSTER == 1;
-  const int tstep = (int)gridDim.x;
-  const int tend = SKIP ? ntiles : niter * tstep;  // tiles of this CTA: blockIdx.x, + tstep, ... < tend
+  constexpr bool SKIP = PP_TC_SKIP && CLUSTER <= 2;
+  const int tstep = (int)gridDim.x;  // a multiple of CLUSTER
+  // tiles of this CTA: blockIdx.x, + tstep, ... < tend; with a cluster the bound is rounded up so that both CTAs of a
+  // pair run the same number of iterations (a tile past the end works on fully masked rows)
+  const int tend = SKIP ? (ntiles + CLUSTER - 1) / CLUSTER * CLUSTER : niter * tstep;
   auto live = [&](int tile) {
     bool any = false;
+    const int base = (CLUSTER == 2) ? (tile & ~1) * 4 : tile * 4;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = tile * 4 + i;
+    for (int i = 0; i < 4 * (CLUSTER == 2 ? 2 : 1); ++i) {
+      const int r = base + i;
       if (r < R) any |= a.msum[r % a.G] != 0.f;
     }
     return any;

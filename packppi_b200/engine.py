@@ -17,6 +17,7 @@ TOP_K = 32
 # From this many residues per complex the kNN graph is built with the cell-list kernel instead of the O(L^2) scan.
 CELL_LIST_MIN_L = int(os.environ.get("PACKPPI_B200_CELL_LIST_MIN_L", "1024"))
 GRAPH_ROWS_MAX = int(os.environ.get("PACKPPI_B200_GRAPH_ROWS", "16384"))
+NODE_CLUSTER = int(os.environ.get("PACKPPI_B200_NODE_CLUSTER", "1"))  # CTAs per cluster of the node-message kernel
 
 
 def _f32(t, dev):
@@ -255,6 +256,11 @@ class Engine:
                           ws.hE, 1 if edge else 0, ws.wsA, ws.wsN, ws.wsP, ws.wsAcc, kernels=5 if edge else 3)
                 continue
             tcp = (3 if self.mode == "f16x3" else 1, self.cluster)
+            # node-message kernel as a cluster of 2 (each CTA fetches half of every weight image and multicasts it):
+            # 0.549 -> 0.490 ms on an unpadded micro-batch (tools/probe_perf.py), but on the benchmark's ragged sweep
+            # the lockstep of the pair costs more than the halved weight fetch saves (6.17 -> 6.10 M residue.steps/s
+            # with pair-granular padding skip), so the default stays 1
+            tcp_node = (tcp[0], max(self.cluster, NODE_CLUSTER))
             # the five kernels of a layer through their own entry points (instrumented fp32 mode, tensor-core modes)
             node_tc = self.mode != "fp32"  # residue prologue on the tensor cores
             pre = lambda path: (  # noqa: E731
@@ -267,7 +273,7 @@ class Engine:
                           ws.wsAcc, rows=S * G)
             else:
                 _lib.call("pp_ipmp_edge_tc", W, layer, 0, self.wtc[layer, 0], *common, graph.msum, G, K, S, hE_in, shared, ws.wsA,
-                          ws.wsN, ws.wsP, ws.wsAcc, *tcp, self.overflow, rows=S * G, tag="node")
+                          ws.wsN, ws.wsP, ws.wsAcc, *tcp_node, self.overflow, rows=S * G, tag="node")
             if self.mode == "fp32" or self.node_epilogue == "ffma":
                 _lib.call("pp_ipmp_node_post", W, layer, *common, graph.msum, *size, ws.wsAcc, ws.hV, rows=S * G)
             else:
