@@ -180,6 +180,19 @@ class Engine:
         self.node_epilogue = node_epilogue
         if mode not in self.MODES:
             raise ValueError(f"mode must be one of {self.MODES}")
+        if mode != "fp32":
+            # LayerNorm outputs are the one operand class the kernels split without tracking (|LN(x)| <= |gain| *
+            # sqrt(127) + |bias|): make sure no checkpoint can push them out of the fp16 range
+            worst = 0.0
+            for k, v in state_dict.items():
+                if "norm" in k and k.endswith(".weight"):
+                    b = state_dict.get(k[:-len("weight")] + "bias")
+                    worst = max(worst, float(v.abs().max()) * math.sqrt(127.0) + (float(b.abs().max()) if b is not None else 0.0))
+            if worst > 32768.0:
+                import warnings
+                warnings.warn(f"packppi_b200: LayerNorm outputs of this checkpoint can reach {worst:.3g}, outside the "
+                              "fp16 range of the split-fp16 tensor-core mode; using the fp32 CUDA-core kernels")
+                mode = "fp32"
         self.mode, self.cluster = mode, int(cluster)
         Engine._serial += 1
         self.serial = Engine._serial  # identifies this set of packed weights (keys of captured CUDA graphs); not id():
