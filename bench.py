@@ -43,7 +43,7 @@ if ROOT not in sys.path:
 
 N_SAMPLES = 8
 N_ODE = 30
-MICRO = 8
+MICRO = int(os.environ.get("PP_BENCH_MICRO", "8"))  # complexes per micro-batch
 # arithmetic of the message-passing GEMMs per execution mode (the `dtype` key of the line)
 DTYPE = {"f16x3": "f32 via 3x split-f16 tensor-core products (fp32 accumulate, fp32-grade)", "fp32": "f32",
          "f16": "f16 inputs, f32 accumulate"}

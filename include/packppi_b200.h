@@ -106,13 +106,16 @@ int pp_ipmp_edge_edge(const float* weights, int64_t layer, const float* geo, con
  * overflow (device int32, may be NULL; the same argument of pp_ipmp_node_pre_tc / pp_ipmp_node_post_tc32): the split
  * into fp16 halves has no per-tile scale, so an activation above 65504 becomes inf, the product NaN, and a ReLU would
  * turn that into a plausible 0.  A kernel that splits such a value ORs 1 into *overflow (never clears it): the caller
- * zeroes the flag, reads it after the pass and repeats the work in fp32 if it is set. */
+ * zeroes the flag, reads it after the pass and repeats the work in fp32 if it is set.
+ * live_tiles / n_live (device, may be NULL): ids of the tiles (4 consecutive rows of the S*G) that hold at least one
+ * residue with msum != 0, in ascending order, and their count; the persistent CTAs then take list positions b, b + grid,
+ * ... instead of testing tiles b, b + grid, ... for liveness, which balances ragged, padded batches (+-1 tile). */
 int64_t pp_tc_stream_floats(void);
 int pp_ipmp_edge_tc(const float* weights, int64_t layer, int64_t path, const float* wstream, const float* geo,
                     const int32_t* nbr, const float* mask_attend, const float* msum, int64_t G, int64_t K,
                     int64_t S, const float* hE_in, int64_t he_shared, const float* wsA, const float* wsN,
                     const float* wsP, float* out, int64_t passes, int64_t cluster, int32_t* overflow,
-                    pp_stream_t stream);
+                    const int32_t* live_tiles, const int32_t* n_live, pp_stream_t stream);
 
 /* pp_ipmp_node_post on the tensor cores with fp32-grade ("promoted") accumulation: every K = 16 step of a GEMM goes
  * into a fresh TMEM accumulator and the row threads sum the steps in fp32 registers, because the tensor core's own

@@ -87,6 +87,8 @@ struct Args {
   const float* hE_in; int he_shared;
   const float *A, *Nn, *pglob;
   const float* msum;                 // mean attention mask [G]: 0 marks a padding residue
+  const int* live_list;              // optional: compacted ids of the live tiles [n_live (+ padding)] ...
+  const int* n_live;                 // ... and their number (device scalar)
   float* out;             // node path: accsum [R][128]; edge path: hE_out [R][K][128]
   int* overflow;              // optional: set to 1 if an activation left the fp16 range (see umma.cuh)
   unsigned long long* trace;  // optional: clock64 stamps of one tile of CTA 0 (pp_set_tc_trace), else null
@@ -208,7 +210,16 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
   const int tstep = (int)gridDim.x;  // a multiple of CLUSTER
   // tiles of this CTA: blockIdx.x, + tstep, ... < tend; with a cluster the bound is rounded up so that both CTAs of a
   // pair run the same number of iterations (a tile past the end works on fully masked rows)
-  const int tend = SKIP ? (ntiles + CLUSTER - 1) / CLUSTER * CLUSTER : niter * tstep;
+  // With a compacted list of the live tiles (a.live_list, built once per graph and sample count) the loop variable
+  // `tile` of every role is a POSITION in that list and tile_id() maps it to the tile: CTA b takes positions b,
+  // b + grid, ... so the live tiles are spread evenly (+-1) over the CTAs.  Walking tile = b, b + grid, ... and testing
+  // liveness instead (the fallback without a list) leaves up to 18 % more tiles on the fullest CTA than on the average
+  // one when a ragged micro-batch is heavily padded, because runs of live tiles alias with the grid size.
+  const int* const ll = a.live_list;
+  const int n_live = ll ? *a.n_live : 0;
+  const int tend = ll ? (n_live + CLUSTER - 1) / CLUSTER * CLUSTER
+                      : (SKIP ? (ntiles + CLUSTER - 1) / CLUSTER * CLUSTER : niter * tstep);
+  auto tile_id = [&](int t) { return ll ? (t < n_live ? ll[t] : ntiles) : t; };  // past the end: fully masked rows
   auto live = [&](int tile) {
     bool any = false;
     const int base = (CLUSTER == 2) ? (tile & ~1) * 4 : tile * 4;
@@ -220,7 +231,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
     return any;
   };
   auto next_tile = [&](int tile) {
-    if (SKIP) while (tile < tend && !live(tile)) tile += tstep;
+    if (SKIP && !ll) while (tile < tend && !live(tile)) tile += tstep;
     return tile;
   };
 
@@ -287,7 +298,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
       const uint32_t box_bytes = (uint32_t)min(K, 32) * 128;
       uint32_t free_phase = 0;
       auto load_tile = [&](int tile) {
-        const int r0 = tile * 4;
+        const int r0 = tile_id(tile) * 4;
         const int nv = max(0, min(4, R - r0));  // residues of the tile that exist
         mbar_arrive_expect_tx(stage_full, (uint32_t)nv * 4 * box_bytes);
         for (int i = 0; i < nv; ++i) {
@@ -307,7 +318,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
           if (nxt < tend) load_tile(nxt);
           while (cur < tend) {
             wait_workers();  // result rows of tile `cur` are in the buffer (and tile `nxt` has been read out of it)
-            const int r0 = cur * 4;
+            const int r0 = tile_id(cur) * 4;
             const int nv = max(0, min(4, R - r0));  // rows k >= K are clipped by the tensor map
             for (int i = 0; i < nv; ++i)
               for (int c = 0; c < 4; ++c) tma_store_box(&tm_out, c * 32, r0 + i, stage + ((c * 4 + i) << 12));
@@ -444,7 +455,7 @@ edge_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_in, const __
     };
     auto row_ctx = [&](int tile) {
       RowCtx c;
-      c.r = tile * 4 + rl;
+      c.r = tile_id(tile) * 4 + rl;
       c.in_range = c.r < R && k < K;
       c.rr = min(c.r, R - 1);
       const int s = c.rr / a.G;
@@ -903,7 +914,7 @@ extern "C" int pp_ipmp_edge_tc(const float* weights, int64_t layer, int64_t path
                                const float* geo, const int32_t* nbr, const float* mask_attend, const float* msum,
                                int64_t G, int64_t K, int64_t S, const float* hE_in, int64_t he_shared, const float* wsA, const float* wsN,
                                const float* wsP, float* out, int64_t passes, int64_t cluster, int32_t* overflow,
-                               cudaStream_t stream) {
+                               const int32_t* live_tiles, const int32_t* n_live, cudaStream_t stream) {
   PP_REQUIRE(weights && wstream && geo && nbr && mask_attend && msum && hE_in && wsA && wsN && wsP && out,
              "null pointer");
   PP_REQUIRE(layer >= 0 && layer < 3 && (path == 0 || path == 1), "layer / path out of range");
@@ -924,6 +935,9 @@ extern "C" int pp_ipmp_edge_tc(const float* weights, int64_t layer, int64_t path
   a.A = wsA; a.Nn = wsN; a.pglob = wsP;
   a.out = out;
   a.overflow = overflow;
+  a.live_list = live_tiles;
+  a.n_live = live_tiles ? n_live : nullptr;
+  PP_REQUIRE(!live_tiles || n_live, "live_tiles needs n_live");
   a.trace = path == g_tc_trace_path ? g_tc_trace : nullptr;  // the trace follows one of the two kernels
   a.trace_it = g_tc_trace_it;
   int rc;

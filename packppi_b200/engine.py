@@ -17,6 +17,7 @@ TOP_K = 32
 # From this many residues per complex the kNN graph is built with the cell-list kernel instead of the O(L^2) scan.
 CELL_LIST_MIN_L = int(os.environ.get("PACKPPI_B200_CELL_LIST_MIN_L", "1024"))
 GRAPH_ROWS_MAX = int(os.environ.get("PACKPPI_B200_GRAPH_ROWS", "16384"))
+USE_LIVE_LIST = os.environ.get("PACKPPI_B200_LIVE_LIST", "1") != "0"  # compacted live-tile list for the tc kernels
 NODE_CLUSTER = int(os.environ.get("PACKPPI_B200_NODE_CLUSTER", "1"))  # CTAs per cluster of the node-message kernel
 
 
@@ -69,6 +70,7 @@ class Graph:
         self.X = _f32(X, dev).clone()
         self.mask = _f32(residue_mask, dev).clone()
         self._cells = None
+        self._live = {}
         self._replay = {}  # captured CUDA graphs of the sampling loop, keyed by (S, steps, ...)
         self._seen = set()
         G, K = self.G, self.K
@@ -96,6 +98,32 @@ class Graph:
         else:
             _lib.call("pp_knn_build", self.X, self.mask, self.B, self.L, self.K, *outs)
         _lib.call("pp_geometry_build", self.X, self.G, self.geo)
+
+    def _live_compute(self, S):
+        dev = self.msum.device
+        rows = (self.msum != 0).repeat(S)
+        nt = (rows.numel() + 3) // 4
+        padded = torch.zeros(nt * 4, dtype=torch.bool, device=dev)
+        padded[:rows.numel()] = rows
+        live = padded.view(nt, 4).any(1)
+        pos = torch.cumsum(live, 0) - 1
+        ids = torch.full((nt + 2,), nt, dtype=torch.int32, device=dev)
+        ids.scatter_(0, torch.where(live, pos, torch.full_like(pos, nt + 1)), torch.arange(nt, dtype=torch.int32, device=dev))
+        ids[nt + 1] = nt  # the slot the dead tiles were scattered to
+        return ids, live.sum().to(torch.int32).reshape(1)
+
+    def live_tiles(self, S):
+        """(ids int32 [ntiles + 2], count int32 [1]) of the 4-row tiles of the S*G rows that hold a residue with
+        msum != 0 (anything else is padding the tensor-core kernels skip), ascending; entries past the count point one
+        past the last tile.  Built with a handful of stream-ordered torch ops, no host synchronisation; cached per S.
+        The tensors keep their addresses for the life of the Graph (captured CUDA graphs hold them): `rebuild`
+        refills them in place."""
+        if getattr(self, "_live", None) is None:
+            self._live = {}
+        hit = self._live.get(S)
+        if hit is None:
+            hit = self._live[S] = self._live_compute(S)
+        return hit
 
     def rebuild(self, X, residue_mask):
         """Same shape, new complex: refill the existing buffers in place (pointers stay valid for captured graphs)."""
@@ -269,6 +297,7 @@ class Engine:
                           ws.hE, 1 if edge else 0, ws.wsA, ws.wsN, ws.wsP, ws.wsAcc, kernels=5 if edge else 3)
                 continue
             tcp = (3 if self.mode == "f16x3" else 1, self.cluster)
+            live = graph.live_tiles(S) if USE_LIVE_LIST and hasattr(graph, "live_tiles") else (None, None)
             # node-message kernel as a cluster of 2 (each CTA fetches half of every weight image and multicasts it):
             # 0.549 -> 0.490 ms on an unpadded micro-batch (tools/probe_perf.py), but on the benchmark's ragged sweep
             # the lockstep of the pair costs more than the halved weight fetch saves (6.17 -> 6.10 M residue.steps/s
@@ -286,7 +315,7 @@ class Engine:
                           ws.wsAcc, rows=S * G)
             else:
                 _lib.call("pp_ipmp_edge_tc", W, layer, 0, self.wtc[layer, 0], *common, graph.msum, G, K, S, hE_in, shared, ws.wsA,
-                          ws.wsN, ws.wsP, ws.wsAcc, *tcp_node, self.overflow, rows=S * G, tag="node")
+                          ws.wsN, ws.wsP, ws.wsAcc, *tcp_node, self.overflow, *live, rows=S * G, tag="node")
             if self.mode == "fp32" or self.node_epilogue == "ffma":
                 _lib.call("pp_ipmp_node_post", W, layer, *common, graph.msum, *size, ws.wsAcc, ws.hV, rows=S * G)
             else:
@@ -299,7 +328,7 @@ class Engine:
                               ws.hE, rows=S * G)
                 else:
                     _lib.call("pp_ipmp_edge_tc", W, layer, 1, self.wtc[layer, 1], *common, graph.msum, G, K, S, hE_in, shared,
-                              ws.wsA, ws.wsN, ws.wsP, ws.hE, *tcp, self.overflow, rows=S * G, tag="edge")
+                              ws.wsA, ws.wsN, ws.wsP, ws.hE, *tcp, self.overflow, *live, rows=S * G, tag="edge")
         return ws.hV
 
     def network(self, graph, batch, chi, t):

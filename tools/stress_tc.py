@@ -86,20 +86,20 @@ def kernels(n=100, passes=3):
 
     acc = torch.zeros_like(ws.wsAcc)
     rep("node message, shared h_E0", lambda: _lib.call("pp_ipmp_edge_tc", W, 0, 0, wtc[0, 0], *common, G, K, S, graph.hE0, 1,
-                                                       ws.wsA, ws.wsN, ws.wsP, acc, passes, 1, None), lambda: acc)
+                                                       ws.wsA, ws.wsN, ws.wsP, acc, passes, 1, None, None, None), lambda: acc)
     hin = ws.hE.clone()
     rep("node message, per-sample h_E", lambda: _lib.call("pp_ipmp_edge_tc", W, 1, 0, wtc[1, 0], *common, G, K, S, hin, 0,
-                                                          ws.wsA, ws.wsN, ws.wsP, acc, passes, 1, None), lambda: acc)
+                                                          ws.wsA, ws.wsN, ws.wsP, acc, passes, 1, None, None, None), lambda: acc)
     hout = torch.zeros_like(ws.hE)
     rep("edge update, shared h_E0", lambda: _lib.call("pp_ipmp_edge_tc", W, 0, 1, wtc[0, 1], *common, G, K, S, graph.hE0, 1,
-                                                      ws.wsA, ws.wsN, ws.wsP, hout, passes, 1, None), lambda: hout)
+                                                      ws.wsA, ws.wsN, ws.wsP, hout, passes, 1, None, None, None), lambda: hout)
     rep("edge update, separate out", lambda: _lib.call("pp_ipmp_edge_tc", W, 1, 1, wtc[1, 1], *common, G, K, S, hin, 0,
-                                                       ws.wsA, ws.wsN, ws.wsP, hout, passes, 1, None), lambda: hout)
+                                                       ws.wsA, ws.wsN, ws.wsP, hout, passes, 1, None, None, None), lambda: hout)
     work = hin.clone()
 
     def inplace():
         work.copy_(hin)
-        _lib.call("pp_ipmp_edge_tc", W, 1, 1, wtc[1, 1], *common, G, K, S, work, 0, ws.wsA, ws.wsN, ws.wsP, work, passes, 1, None)
+        _lib.call("pp_ipmp_edge_tc", W, 1, 1, wtc[1, 1], *common, G, K, S, work, 0, ws.wsA, ws.wsN, ws.wsP, work, passes, 1, None, None, None)
     rep("edge update, in place", inplace, lambda: work)
     hv0 = ws.hV.clone()
     hv = hv0.clone()
