@@ -109,7 +109,9 @@ int pp_ipmp_edge_edge(const float* weights, int64_t layer, const float* geo, con
  * zeroes the flag, reads it after the pass and repeats the work in fp32 if it is set.
  * live_tiles / n_live (device, may be NULL): ids of the tiles (4 consecutive rows of the S*G) that hold at least one
  * residue with msum != 0, in ascending order, and their count; the persistent CTAs then take list positions b, b + grid,
- * ... instead of testing tiles b, b + grid, ... for liveness, which balances ragged, padded batches (+-1 tile). */
+ * ... instead of testing tiles b, b + grid, ... for liveness, which balances ragged, padded batches (+-1 tile).  The
+ * same pair of arguments of pp_ipmp_node_pre_tc / pp_ipmp_node_post_tc32 lists live tiles of 128 rows; their output
+ * rows in tiles of pure padding are then left untouched. */
 int64_t pp_tc_stream_floats(void);
 int pp_ipmp_edge_tc(const float* weights, int64_t layer, int64_t path, const float* wstream, const float* geo,
                     const int32_t* nbr, const float* mask_attend, const float* msum, int64_t G, int64_t K,
@@ -123,7 +125,7 @@ int pp_ipmp_edge_tc(const float* weights, int64_t layer, int64_t path, const flo
  * [S*G][128] is updated in place (reference layers.py:127-132). */
 int pp_ipmp_node_post_tc32(const float* weights, int64_t layer, const float* wstream, const float* msum,
                            const float* residue_mask, int64_t G, int64_t K, int64_t S, const float* wsAcc, float* hV,
-                           int32_t* overflow, pp_stream_t stream);
+                           int32_t* overflow, const int32_t* live_tiles, const int32_t* n_live, pp_stream_t stream);
 
 /* Tensor-core version of pp_ipmp_node_pre (reference layers.py:72-77,91 and the h_V_i / h_V_j columns of W_in):
  * tile = 128 residue rows, the three weight matrices resident in shared memory as fp16 (hi, lo) images.
@@ -131,7 +133,7 @@ int pp_ipmp_node_post_tc32(const float* weights, int64_t layer, const float* wst
 int64_t pp_tc_pre_stream_floats(void);
 int pp_ipmp_node_pre_tc(const float* weights, int64_t layer, int64_t path, const float* wstream, const float* geo,
                         int64_t G, int64_t S, const float* hV, float* wsA, float* wsN, float* wsP,
-                        int32_t* overflow, pp_stream_t stream);
+                        int32_t* overflow, const int32_t* live_tiles, const int32_t* n_live, pp_stream_t stream);
 
 /* Diagnostics: later pp_ipmp_edge_tc launches write clock64() stamps of the phase boundaries of their first tile
  * (CTA 0, one worker thread) into trace (device memory, >= 32 uint64); NULL switches it off. */

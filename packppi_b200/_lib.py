@@ -27,8 +27,8 @@ SIGNATURES = {
     "pp_ipmp_node_post": "p" "i" "ppppp" "iii" "pp" "s",
     "pp_ipmp_edge_edge": "p" "i" "pppp" "iii" "p" "i" "pppp" "s",
     "pp_ipmp_edge_tc": "p" "ii" "ppppp" "iii" "p" "i" "pppp" "ii" "p" "pp" "s",
-    "pp_ipmp_node_pre_tc": "p" "ii" "pp" "ii" "pppp" "p" "s",
-    "pp_ipmp_node_post_tc32": "p" "i" "ppp" "iii" "pp" "p" "s",
+    "pp_ipmp_node_pre_tc": "p" "ii" "pp" "ii" "pppp" "p" "pp" "s",
+    "pp_ipmp_node_post_tc32": "p" "i" "ppp" "iii" "pp" "p" "pp" "s",
     "pp_decode_step": "pp" "ii" "p" "i" "ff" "ppp" "ppp" "f" "ii" "s",
     "pp_atom14_fwd": "pppp" "ii" "p" "s",
     "pp_clash_neighbours": "ppppp" "ii" "f" "i" "pppp" "s",

@@ -58,6 +58,8 @@ struct Args {
   float in_scale;             // 1 / K
   float* hV;                  // [R][128], updated in place
   int* overflow;              // optional overflow flag (umma.cuh: report_overflow)
+  const int* live_list;       // optional: ids of the live 128-row tiles ...
+  const int* n_live;          // ... and their number (device scalar)
 };
 
 __device__ __forceinline__ void put_chunk(uint8_t* slot, int m, const float* v, float& amax) {
@@ -92,6 +94,10 @@ __global__ void __launch_bounds__(kThreads, 1) node_post_tc_kernel(const Args a)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int R = a.R;
   const int ntiles = (R + kRows - 1) / kRows;
+  // with a compacted list of the live 128-row tiles (tiles that hold at least one unmasked residue) every role walks
+  // list positions instead of tile numbers: padding tiles of a ragged batch are never touched (their output rows keep
+  // whatever they held; nothing unmasked reads them)
+  const int nwork = a.live_list ? *a.n_live : ntiles;
 
   if (tid == 0) {
     for (int i = 0; i < kSA; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
@@ -121,7 +127,7 @@ __global__ void __launch_bounds__(kThreads, 1) node_post_tc_kernel(const Args a)
       int idx = 0;
       uint32_t phase = 1;
       const uint8_t* base = reinterpret_cast<const uint8_t*>(a.wstream);
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < nwork; tile += gridDim.x) {
         for (int blk = -1; blk < 8; ++blk) {
           const uint8_t* src = base + (blk < 0 ? 0 : (size_t)(1 + order[blk]) * 4 * kSlotBytes);
           for (int c = 0; c < 4; ++c) {
@@ -178,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) node_post_tc_kernel(const Args a)
       if (++ib == kSB) { ib = 0; pb ^= 1; }
       if (ss && ++ia == kSA) { ia = 0; pa ^= 1; }
     };
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < nwork; tile += gridDim.x) {
       for (int c = 0; c < 4; ++c) chunk(true, 0);  // W3
       mbar_wait(e_ready, pe); pe ^= 1;
       fence_after_sync();
@@ -254,7 +260,8 @@ __global__ void __launch_bounds__(kThreads, 1) node_post_tc_kernel(const Args a)
       }
     };
 
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int pos = blockIdx.x; pos < nwork; pos += gridDim.x) {
+      const int tile = a.live_list ? a.live_list[pos] : pos;
       const int r = tile * kRows + m;
       const bool in = r < R;
       const int rr = min(r, R - 1);
@@ -390,7 +397,8 @@ using namespace pp;
 // pp_ipmp_node_post; wstream = operand images of path 2 of this layer (weights.py: pack_tc_stream).
 extern "C" int pp_ipmp_node_post_tc32(const float* weights, int64_t layer, const float* wstream, const float* msum,
                                       const float* residue_mask, int64_t G, int64_t K, int64_t S, const float* wsAcc,
-                                      float* hV, int32_t* overflow, cudaStream_t stream) {
+                                      float* hV, int32_t* overflow, const int32_t* live_tiles, const int32_t* n_live,
+                                      cudaStream_t stream) {
   PP_REQUIRE(weights && wstream && msum && residue_mask && wsAcc && hV, "null pointer");
   PP_REQUIRE(layer >= 0 && layer < 3, "layer out of range");
   PP_REQUIRE(G > 0 && S > 0 && K > 0 && K <= PP_KMAX, "bad sizes");
@@ -406,6 +414,9 @@ extern "C" int pp_ipmp_node_post_tc32(const float* weights, int64_t layer, const
   a.accsum = wsAcc; a.in_scale = 1.f / (float)K;
   a.hV = hV;
   a.overflow = overflow;
+  a.live_list = live_tiles;
+  a.n_live = live_tiles ? n_live : nullptr;
+  PP_REQUIRE(!live_tiles || n_live, "live_tiles needs n_live");
   cudaError_t e = cudaFuncSetAttribute(post::node_post_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post::kSmem);
   if (e != cudaSuccess) {
     snprintf(g_last_error, sizeof(g_last_error), "node_post_tc_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));

@@ -44,6 +44,8 @@ struct Args {
   const float* hV;       // [R][128]
   float *A, *Nn, *P;     // wsA, wsN [R][128], wsP [R][24]
   int* overflow;         // optional overflow flag (umma.cuh: report_overflow)
+  const int* live_list;  // optional: ids of the live 128-row tiles ...
+  const int* n_live;     // ... and their number (device scalar)
 };
 
 __device__ __forceinline__ void put_chunk(uint8_t* slot, int m, const float* v, float& amax) {
@@ -77,6 +79,10 @@ __global__ void __launch_bounds__(kThreads, 1) node_pre_tc_kernel(const Args a) 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int R = a.R;
   const int ntiles = (R + kRows - 1) / kRows;
+  // with a compacted list of the live 128-row tiles (tiles that hold at least one unmasked residue) every role walks
+  // list positions instead of tile numbers: padding tiles of a ragged batch are never touched (their output rows keep
+  // whatever they held; nothing unmasked reads them)
+  const int nwork = a.live_list ? *a.n_live : ntiles;
 
   if (tid == 0) {
     mbar_init(w_full, 1);
@@ -122,7 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1) node_pre_tc_kernel(const Args a) 
                         (fresh && p == 0 && kk == 0) ? 0u : 1u);
         }
       };
-      for (int tile = blockIdx.x, it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+      for (int tile = blockIdx.x, it = 0; tile < nwork; tile += gridDim.x, ++it) {
         if (it > 0) { mbar_wait(tile_done, td_phase); td_phase ^= 1; fence_after_sync(); }
         for (int c = 0; c < 5; ++c, ++q) {
           const int slot = q % kSA;
@@ -166,7 +172,8 @@ __global__ void __launch_bounds__(kThreads, 1) node_pre_tc_kernel(const Args a) 
 #pragma unroll
       for (int i = 0; i < 32; ++i) dst[i] = __uint_as_float(u[i]);
     };
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int pos = blockIdx.x; pos < nwork; pos += gridDim.x) {
+      const int tile = a.live_list ? a.live_list[pos] : pos;
       const int r = tile * kRows + m;
       const bool in = r < R;
       const int rr = min(r, R - 1);
@@ -255,7 +262,8 @@ extern "C" int64_t pp_tc_pre_stream_floats() { return pre::kStreamFloats; }
 //   wstream: operand images of this layer and path, pp_tc_pre_stream_floats() floats (weights.py: pack_pre_stream)
 extern "C" int pp_ipmp_node_pre_tc(const float* weights, int64_t layer, int64_t path, const float* wstream,
                                    const float* geo, int64_t G, int64_t S, const float* hV, float* wsA, float* wsN,
-                                   float* wsP, int32_t* overflow, cudaStream_t stream) {
+                                   float* wsP, int32_t* overflow, const int32_t* live_tiles, const int32_t* n_live,
+                                   cudaStream_t stream) {
   PP_REQUIRE(weights && wstream && geo && hV && wsA && wsN && wsP, "null pointer");
   PP_REQUIRE(layer >= 0 && layer < 3 && (path == 0 || path == 1), "layer / path out of range");
   PP_REQUIRE(G > 0 && S > 0, "bad sizes");
@@ -267,6 +275,9 @@ extern "C" int pp_ipmp_node_pre_tc(const float* weights, int64_t layer, int64_t 
   a.B1 = Lb + (path ? PP_OFF(L0_E_B1) : PP_OFF(L0_N_B1));
   a.hV = hV; a.A = wsA; a.Nn = wsN; a.P = wsP;
   a.overflow = overflow;
+  a.live_list = live_tiles;
+  a.n_live = live_tiles ? n_live : nullptr;
+  PP_REQUIRE(!live_tiles || n_live, "live_tiles needs n_live");
   cudaError_t e = cudaFuncSetAttribute(pre::node_pre_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre::kSmem);
   if (e != cudaSuccess) {
     snprintf(g_last_error, sizeof(g_last_error), "node_pre_tc_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));

@@ -99,30 +99,30 @@ class Graph:
             _lib.call("pp_knn_build", self.X, self.mask, self.B, self.L, self.K, *outs)
         _lib.call("pp_geometry_build", self.X, self.G, self.geo)
 
-    def _live_compute(self, S):
+    def _live_compute(self, S, per=4):
         dev = self.msum.device
         rows = (self.msum != 0).repeat(S)
-        nt = (rows.numel() + 3) // 4
-        padded = torch.zeros(nt * 4, dtype=torch.bool, device=dev)
+        nt = (rows.numel() + per - 1) // per
+        padded = torch.zeros(nt * per, dtype=torch.bool, device=dev)
         padded[:rows.numel()] = rows
-        live = padded.view(nt, 4).any(1)
+        live = padded.view(nt, per).any(1)
         pos = torch.cumsum(live, 0) - 1
         ids = torch.full((nt + 2,), nt, dtype=torch.int32, device=dev)
         ids.scatter_(0, torch.where(live, pos, torch.full_like(pos, nt + 1)), torch.arange(nt, dtype=torch.int32, device=dev))
         ids[nt + 1] = nt  # the slot the dead tiles were scattered to
         return ids, live.sum().to(torch.int32).reshape(1)
 
-    def live_tiles(self, S):
-        """(ids int32 [ntiles + 2], count int32 [1]) of the 4-row tiles of the S*G rows that hold a residue with
-        msum != 0 (anything else is padding the tensor-core kernels skip), ascending; entries past the count point one
-        past the last tile.  Built with a handful of stream-ordered torch ops, no host synchronisation; cached per S.
+    def live_tiles(self, S, per=4):
+        """(ids int32 [ntiles + 2], count int32 [1]) of the `per`-row tiles (4: per-edge kernels, 128: per-residue
+        kernels) of the S*G rows that hold a residue with msum != 0 (anything else is padding the tensor-core kernels
+        skip), ascending; entries past the count point one past the last tile.  Built with a handful of stream-ordered torch ops, no host synchronisation; cached per S.
         The tensors keep their addresses for the life of the Graph (captured CUDA graphs hold them): `rebuild`
         refills them in place."""
         if getattr(self, "_live", None) is None:
             self._live = {}
-        hit = self._live.get(S)
+        hit = self._live.get((S, per))
         if hit is None:
-            hit = self._live[S] = self._live_compute(S)
+            hit = self._live[(S, per)] = self._live_compute(S, per)
         return hit
 
     def rebuild(self, X, residue_mask):
@@ -297,7 +297,9 @@ class Engine:
                           ws.hE, 1 if edge else 0, ws.wsA, ws.wsN, ws.wsP, ws.wsAcc, kernels=5 if edge else 3)
                 continue
             tcp = (3 if self.mode == "f16x3" else 1, self.cluster)
-            live = graph.live_tiles(S) if USE_LIVE_LIST and hasattr(graph, "live_tiles") else (None, None)
+            use_list = USE_LIVE_LIST and getattr(graph, "_live", None) is not None
+            live = graph.live_tiles(S) if use_list else (None, None)
+            live128 = graph.live_tiles(S, 128) if use_list else (None, None)
             # node-message kernel as a cluster of 2 (each CTA fetches half of every weight image and multicasts it):
             # 0.549 -> 0.490 ms on an unpadded micro-batch (tools/probe_perf.py), but on the benchmark's ragged sweep
             # the lockstep of the pair costs more than the halved weight fetch saves (6.17 -> 6.10 M residue.steps/s
@@ -307,7 +309,7 @@ class Engine:
             node_tc = self.mode != "fp32"  # residue prologue on the tensor cores
             pre = lambda path: (  # noqa: E731
                 _lib.call("pp_ipmp_node_pre_tc", W, layer, path, self.wpre[layer, path], graph.geo, G, S, ws.hV, ws.wsA,
-                          ws.wsN, ws.wsP, self.overflow, rows=S * G) if node_tc else
+                          ws.wsN, ws.wsP, self.overflow, *live128, rows=S * G) if node_tc else
                 _lib.call("pp_ipmp_node_pre", W, layer, path, *common, *size, ws.hV, ws.wsA, ws.wsN, ws.wsP, rows=S * G))
             pre(0)
             if self.mode == "fp32":
@@ -320,7 +322,7 @@ class Engine:
                 _lib.call("pp_ipmp_node_post", W, layer, *common, graph.msum, *size, ws.wsAcc, ws.hV, rows=S * G)
             else:
                 _lib.call("pp_ipmp_node_post_tc32", W, layer, self.wtc[layer, 2], graph.msum, graph.mask, G, K, S,
-                          ws.wsAcc, ws.hV, self.overflow, rows=S * G)
+                          ws.wsAcc, ws.hV, self.overflow, *live128, rows=S * G)
             if edge:
                 pre(1)
                 if self.mode == "fp32":
@@ -337,6 +339,8 @@ class Engine:
         ws = self.workspace(graph.G, graph.K, S)
         ni = graph.ni if getattr(graph, "ni", None) is not None else self.node_inputs(batch)
         self.forward_layers(graph, ws, ni, chi, t, 1)
+        if self.mode != "fp32":  # tiles of pure padding are skipped by the tensor-core kernels: the API returns zeros there
+            ws.hV.view(S, graph.G, 128).mul_(graph.mask.view(1, graph.G, 1))
         _lib.call("pp_decode_step", self.wblob, ws.hV, graph.G, S, ws.score, 0, 0.0, 0.0, None, None, None, None, None,
                   None, 0.0, 0, 0)
         return ws.score, ws.hV

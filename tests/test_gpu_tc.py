@@ -134,7 +134,7 @@ def test_node_pre_tc_matches_cuda_core_kernel(case):
             out = [torch.full((S * G, n), float("nan"), device=dev) for n in (128, 128, 24)]
             _lib.call("pp_ipmp_node_pre", W, layer, path, graph.geo, graph.nbr, graph.mask_attend, graph.mask, G, K, S,
                       hV, *ref)
-            _lib.call("pp_ipmp_node_pre_tc", W, layer, path, eng.wpre[layer, path], graph.geo, G, S, hV, *out, None)
+            _lib.call("pp_ipmp_node_pre_tc", W, layer, path, eng.wpre[layer, path], graph.geo, G, S, hV, *out, None, None, None)
             torch.cuda.synchronize()
             for name, r, o in zip(("A", "N", "P"), ref, out):
                 scale = max(1.0, r.abs().max().item())
@@ -159,7 +159,7 @@ def test_node_post_tc32_matches_cuda_core_kernel(case):
         ref, out = hV0.clone(), hV0.clone()
         _lib.call("pp_ipmp_node_post", W, layer, graph.geo, graph.nbr, graph.mask_attend, graph.msum, graph.mask, G, K,
                   S, acc, ref)
-        _lib.call("pp_ipmp_node_post_tc32", W, layer, eng.wtc[layer, 2], graph.msum, graph.mask, G, K, S, acc, out, None)
+        _lib.call("pp_ipmp_node_post_tc32", W, layer, eng.wtc[layer, 2], graph.msum, graph.mask, G, K, S, acc, out, None, None, None)
         torch.cuda.synchronize()
         assert torch.isfinite(out).all()
         assert (ref - out).abs().max().item() < 5e-6 * max(1.0, ref.abs().max().item()), layer

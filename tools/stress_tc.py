@@ -106,7 +106,7 @@ def kernels(n=100, passes=3):
 
     def post():
         hv.copy_(hv0)
-        _lib.call("pp_ipmp_node_post_tc32", W, 0, wtc[0, 2], graph.msum, graph.mask, G, K, S, ws.wsAcc, hv, None)
+        _lib.call("pp_ipmp_node_post_tc32", W, 0, wtc[0, 2], graph.msum, graph.mask, G, K, S, ws.wsAcc, hv, None, None, None)
     rep("node epilogue", post, lambda: hv)
 
 
