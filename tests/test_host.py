@@ -402,3 +402,41 @@ def test_interface_mask_and_metric_block_match_the_reference(tmp_path):
     assert set(keys) == set(got) and len(keys) == 16
     for k in keys:
         assert abs(float(got[k]) - float(z["1brs_metric_" + k])) <= 1e-5 * max(1.0, abs(float(z["1brs_metric_" + k]))), k
+
+
+def test_live_tile_lists_are_compact_and_ordered():
+    """engine.Graph._live_compute: ids of the 4-row / 128-row tiles that hold a residue with msum != 0, ascending, the
+    tail pointing one past the last tile (what the persistent tensor-core kernels index by position)."""
+    from packppi_b200.engine import Graph
+    rng = np.random.default_rng(3)
+    for G, S, per in ((13, 2, 4), (700, 3, 4), (700, 3, 128), (5, 1, 128), (1024, 8, 128)):
+        msum = torch.from_numpy((rng.random(G) < 0.4).astype(np.float32))
+        msum[G // 3:G // 2] = 0  # a run of padding
+        g = Graph.__new__(Graph)
+        g.msum = msum
+        ids, cnt = g._live_compute(S, per)
+        rows = np.tile(msum.numpy() != 0, S)
+        nt = (len(rows) + per - 1) // per
+        pad = np.zeros(nt * per, bool)
+        pad[:len(rows)] = rows
+        want = np.nonzero(pad.reshape(nt, per).any(1))[0]
+        assert int(cnt) == len(want) and ids.dtype == torch.int32 and ids.numel() == nt + 2
+        assert np.array_equal(ids[:len(want)].numpy(), want)
+        assert (ids[len(want):] == nt).all()
+
+
+def test_bench_sample_selection_is_stratified():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class Item:
+        def __init__(self, n):
+            self.max_size = n
+
+    items = [Item(n) for n in (500, 210, 790, 330, 640, 450, 270, 720)]
+    picks = [it.max_size for it in bench.stratified(items, 4)]
+    assert picks == [270, 450, 640, 790] or picks == sorted(picks)  # one per length quartile, ascending
+    assert len(set(picks)) == 4 and min(picks) < 400 < max(picks)
+    assert [it.max_size for it in bench.stratified(items, 1)] == [500]
