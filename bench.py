@@ -53,8 +53,9 @@ EDGE_KERNEL_FLOP_PER_RES = 32 * 2 * (168 * 128 + 128 * 128 + 128 * 128 + 2 * 128
 # algorithmic HBM bytes of the same launch per residue row: read h_E (K*128*4), write h_E (K*128*4), A, N gathers
 EDGE_KERNEL_BYTES_PER_RES = 2 * 32 * 128 * 4 + 2 * 128 * 4 + 24 * 4
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per valid residue row of the same kernel, from the
-# `ncu --set full` capture in profiles/r01_tc_f16x3_ncu_raw.csv: 966.6 MB for a launch over 29 616 valid rows
-NCU_EDGE_TRAFFIC_PER_RES = {"f16x3": 966.555e6 / 29616}
+# `ncu --set full` capture in profiles/r02_edge_tc_ncu_raw.csv: 520.9 MB read + 444.5 MB written for a launch over
+# 29 616 valid rows (round 1: 966.6 MB - unchanged, the traffic is the algorithmic h_E read + write)
+NCU_EDGE_TRAFFIC_PER_RES = {"f16x3": (520.866304e6 + 444.490752e6) / 29616}
 
 
 def measured_peaks():
@@ -651,7 +652,7 @@ def main():
                 "traffic": (NCU_EDGE_TRAFFIC_PER_RES[mode] * tot_rows / len(k_ms)
                             if mode in NCU_EDGE_TRAFFIC_PER_RES else None),
                 "traffic_note": "bytes per launch = ncu DRAM bytes per valid residue row (profiles/"
-                                "r01_tc_f16x3_ncu_raw.csv) x the average valid rows per launch of this run",
+                                "r02_edge_tc_ncu_raw.csv) x the average valid rows per launch of this run",
                 "algorithmic_bytes_per_launch": EDGE_KERNEL_BYTES_PER_RES * tot_rows / len(k_ms),
                 "avg_launch_ms": tot_ms / len(k_ms), "launches": len(k_ms),
                 "share_of_step": tot_ms / t_pass, "hbm_view": {"achieved_GBps": gbs, "peak_GBps": peaks["hbm"],
