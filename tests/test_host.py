@@ -440,3 +440,36 @@ def test_bench_sample_selection_is_stratified():
     assert picks == [270, 450, 640, 790] or picks == sorted(picks)  # one per length quartile, ascending
     assert len(set(picks)) == 4 and min(picks) < 400 < max(picks)
     assert [it.max_size for it in bench.stratified(items, 1)] == [500]
+
+
+def test_host_tensors_are_refused_unless_staged_and_staging_needs_a_cuda_device():
+    """No CPU implementation: CPU tensors raise RuntimeError; `host_staging` only accepts a CUDA device (it moves the
+    buffers, it does not compute on the host)."""
+    import packppi_b200
+    from packppi_b200 import synthetic
+    b = synthetic.make_complex((6, 5), seed=1)
+    with pytest.raises(RuntimeError):
+        packppi_b200.get_atom14_coords(b.X, b.residue_type, b.BB_D, b.SC_D)
+    with pytest.raises(RuntimeError):
+        packppi_b200.proximal_optimizer(b, b.SC_D, 12.0, 0.5, 1.0, 2)
+    with pytest.raises(RuntimeError):
+        with packppi_b200.host_staging("cpu"):
+            pass
+    from packppi_b200 import components
+    assert components._STAGE_DEVICE is None
+
+
+@pytest.mark.skipif(_ref_data_dir() is None, reason="PDB fixtures of the reference not present")
+def test_interface_mask_without_the_reference_quirk_marks_both_chains():
+    """`as_reference=False` compares every chain's residue numbers with the file's own numbering: both chains of the
+    barnase-barstar complex then have interface residues (the reference's in-place offset leaves the second chain with
+    accidental matches only, which `as_reference=True` reproduces)."""
+    from packppi_b200 import metrics, pdb
+    path = os.path.join(_ref_data_dir(), "1BRS.pdb")
+    prot = pdb.read_pdb(path)
+    chains = np.asarray(prot["chain_id"])
+    fair = metrics.interface_mask(prot, path, as_reference=False).numpy()
+    quirk = metrics.interface_mask(prot, path).numpy()
+    first, second = chains == np.unique(chains)[0], chains == np.unique(chains)[1]
+    assert fair[first].sum() > 20 and fair[second].sum() > 20
+    assert np.array_equal(fair[first], quirk[first]) and quirk[second].sum() < fair[second].sum()
