@@ -278,7 +278,16 @@ class TDiffusionModule(_PackedModule):
             t = t.repeat(lead)  # one time per residue, shared by the samples
         elif t.numel() != chi.shape[0]:
             raise ValueError(f"network: t has {t.numel()} entries; expected B*L = {B * L} or S*B*L = {chi.shape[0]}")
-        score, hV = eng.network(g, batch, chi, t.contiguous())
+        t = t.contiguous()
+        check = eng.mode != "fp32" and self.check_finite
+        if check:
+            eng.overflow.zero_()
+        score, hV = eng.network(g, batch, chi, t)
+        if check and bool(eng.overflow.item()):  # same guard as in `sampling`: an activation left the fp16 range
+            import warnings
+            warnings.warn("packppi_b200: an activation left the fp16 range in the split-fp16 tensor-core mode; repeating "
+                          "this call with the fp32 CUDA-core kernels")
+            score, hV = self._fp32_engine(chi.device).network(g, batch, chi, t)
         shape = (B, L) if lead == 1 else (lead, B, L)
         return score.reshape(*shape, 4).clone(), hV.reshape(*shape, H).clone()
 

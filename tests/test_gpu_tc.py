@@ -251,3 +251,13 @@ def test_fp16_overflow_is_detected_and_redone_in_fp32():
         assert (len([x for x in w if "fp16 range" in str(x.message)]) == 1) == (mode == "f16x3"), mode
     assert torch.isfinite(outs["f16x3"]).all()
     assert torch.equal(outs["f16x3"], outs["fp32"])
+    # the same guard protects `network` (the PackPPI-AP feature-extractor call)
+    B, L = b.X.shape[:2]
+    m.kernel_mode = "f16x3"
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        s16, h16 = m.network(b.to(dev), init, torch.full((B * L,), 0.5, device=dev))
+    assert any("fp16 range" in str(x.message) for x in w)
+    m.kernel_mode = "fp32"
+    s32, h32 = m.network(b.to(dev), init, torch.full((B * L,), 0.5, device=dev))
+    assert torch.equal(s16, s32) and torch.equal(h16, h32)
